@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched 1-D complex FFT hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  The default workload is
+BASELINE.json configs[1]: batched N=2^20 complex-f32 forward FFT, batch 4096, on one B200.  With
+--gpus N>1 (launched by torchrun, one rank per GPU) every rank transforms its own batch of the same
+size (independent transforms, no data-path collective): weak scaling.
+
+Prints ONE JSON line (rank 0).  `value` is whole-job complex samples/s with inputs resident in HBM;
+`e2e` is the same metric through the C-ABI call with HOST (pinned) buffers, copies inside the timed
+region; `roofline` relates the dominant kernel's algorithmic bytes (16 B/sample f32, 32 B/sample
+f64: read once + write once) to the measured HBM peak; `cpu_baseline` is the oracle
+(C restatement of the reference CPU algorithm; the Rust reference cannot be built in this image)
+timed on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, per-GPU batch, real, description)
+    "c1": (1024, 1, "f32", "single 1024-pt c-f32 forward (BASELINE configs[0], correctness gate)"),
+    "c2": (1 << 20, 4096, "f32", "batched N=2^20 c-f32 forward, batch 4096 per GPU (BASELINE configs[1])"),
+    "c3": (1 << 16, 65536, "f64", "batched N=2^16 c-f64 forward, batch 65536 (BASELINE configs[2])"),
+    "c4": (1009, 1 << 20, "f32", "prime N=1009 Bluestein c-f32 forward, batch 2^20 (BASELINE configs[3])"),
+}
+BYTES_PER_SAMPLE = {"f32": 16, "f64": 32}  # algorithmic: read once + write once
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (pynvml)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(n, real, seconds_target=12.0, threads=None):
+    """Oracle (C restatement of the reference CPU path) on the host cores, bounded sample."""
+    from oracle import oracle as O
+    threads = threads or os.cpu_count() or 1
+    dt = np.complex64 if real == "f32" else np.complex128
+    # probe one transform per thread, then size the sample for ~seconds_target of CPU work
+    x = O.fill_input(threads, n, dt)
+    _, sec = O.transform_batch(x, O.FFT, threads)
+    per_thread = max(1, min(int(seconds_target / max(sec, 1e-6)), max(1, (1 << 28) // (n * threads))))
+    batch = per_thread * threads
+    x = O.fill_input(batch, n, dt)
+    _, sec = O.transform_batch(x, O.FFT, threads)
+    return {"value": batch * n / sec, "unit": "complex samples/s", "cores": threads, "kind": "port",
+            "sample": f"{batch} transforms of N={n} ({real}), {per_thread} per thread, out-of-place forward, "
+                      f"{sec:.2f} s; oracle/ = C restatement of the reference algorithm (rustc absent)"}
+
+
+def run_reference(args, n, batch, real, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    dt = np.complex64 if real == "f32" else np.complex128
+    x = O.fill_input(threads, n, dt)
+    _, sec = O.transform_batch(x, O.FFT, threads)
+    # each step: bounded sample so that steps+warmup finish within a few minutes
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    per_thread = max(1, min(int(budget / max(sec, 1e-6)), max(1, (1 << 27) // (n * threads))))
+    sample = per_thread * threads
+    x = O.fill_input(sample, n, dt)
+    for _ in range(args.warmup):
+        O.transform_batch(x, O.FFT, threads)
+    total = 0.0
+    for _ in range(args.steps):
+        _, s = O.transform_batch(x, O.FFT, threads)
+        total += s
+    value = sample * n * args.steps / total
+    base = {"value": value, "unit": "complex samples/s", "cores": threads, "kind": "port",
+            "sample": f"{sample} transforms of N={n} per step ({per_thread} per thread)"}
+    print(json.dumps({
+        "impl": "reference", "metric": "batched 1D FFT complex-samples/sec", "value": value,
+        "unit": "complex samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": real, "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][3], "N": n, "batch_per_gpu": batch,
+                   "note": "reference CPU algorithm (oracle port: rustc/cargo absent from the image), "
+                           "all host threads, bounded sample per step"},
+        "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "complex samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--e2e-batch", type=int, default=0, help="transforms per e2e step (host buffers)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", type=int, default=4, help="transforms checked against the oracle")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n, batch, real, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+
+    if args.impl == "reference":
+        run_reference(args, n, batch, real, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fourier_b200 as fb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    fb.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cdt = torch.complex64 if real == "f32" else torch.complex128
+    plan = fb.create_fft_f32(n) if real == "f32" else fb.create_fft_f64(n)
+    info = plan.info()
+
+    # this rank's shard: transforms [rank*batch, (rank+1)*batch) of the global synthetic batch
+    x = torch.empty((batch, n), dtype=cdt, device="cuda")
+    y = torch.empty_like(x)
+    fb.fill_input(x, first_transform=rank * batch)
+    torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        plan.transform(x, y, fb.Transform.Fft)
+    barrier()
+    launches_per_step = plan.info()["last_launches"]
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            plan.transform(x, y, fb.Transform.Fft)
+        stop.record()
+        barrier()
+    ms = torch.tensor([start.elapsed_time(stop)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    ms_per_step = ms_total / args.steps
+    value = world * batch * n * args.steps / (ms_total * 1e-3)
+
+    # parity spot-check of the timed output against the oracle (identical hash-generated input)
+    verify = {}
+    if rank == 0 and args.verify > 0:
+        from oracle import oracle as O
+        dt = np.complex64 if real == "f32" else np.complex128
+        picks = sorted({0, 1 % batch, batch // 2, batch - 1})[: args.verify]
+        worst = 0.0
+        for b in picks:
+            want = O.transform(O.fill_input(1, n, dt, first_transform=b)[0], O.FFT)
+            got = y[b].cpu().numpy()
+            worst = max(worst, float(np.abs(got - want).max() / np.abs(want).max()))
+        verify = {"transforms_checked": picks, "max_rel_err_vs_oracle": worst,
+                  "tolerance": 1e-5 if real == "f32" else 1e-12}
+
+    # end to end through the C ABI with host (pinned) buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        eb = args.e2e_batch or max(1, min(batch, (2 << 30) // (n * (8 if real == "f32" else 16))))
+        hx = torch.empty((eb, n), dtype=cdt).pin_memory()
+        hy = torch.empty((eb, n), dtype=cdt).pin_memory()
+        hx.copy_(x[:eb])
+        e2e_steps = max(2, min(args.steps, 5))
+        plan.transform(hx, hy, fb.Transform.Fft)  # warm-up (allocates staging)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.transform(hx, hy, fb.Transform.Fft)
+        barrier()
+        dt_s = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt_s, op=dist.ReduceOp.MAX)
+        bytes_step = eb * n * (8 if real == "f32" else 16)
+        e2e = {"value": world * eb * n * e2e_steps / float(dt_s.item()), "unit": "complex samples/s",
+               "h2d_bytes_per_step": bytes_step, "d2h_bytes_per_step": bytes_step,
+               "batch_per_step": eb, "steps": e2e_steps,
+               "note": "fourier_b200_transform_batch_* on pinned host buffers: chunked H2D -> FFT -> D2H pipeline"}
+        if rank == 0 and args.verify > 0:
+            e2e["matches_device_path"] = bool(torch.equal(hy[:1], y[:1].cpu()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    bps = BYTES_PER_SAMPLE[real]
+    achieved = batch * n * bps / (ms_per_step * 1e-3) / 1e9  # per GPU
+    out = {
+        "metric": "batched 1D FFT complex-samples/sec", "value": value, "unit": "complex samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": real, "data": "synthetic",
+        "config": {"workload": desc, "N": n, "batch_per_gpu": batch, "transform": "Fft (forward, out of place)",
+                   "path": info["path_name"], "inner_path": info["inner_path_name"],
+                   "l2": "inputs larger than L2 (no flush needed)" if batch * n * bps // 2 > (256 << 20)
+                   else "inputs smaller than L2: numbers are L2-warm",
+                   "parallelism": f"batch-sharded x{world}, no collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "algorithmic_bytes_per_sample": bps,
+                     "kernel": "whole step (all launches of one batched transform)"},
+        "gpu_launches": int(launches_per_step) * args.steps,
+        "clocks": clocks.summary(),
+        "verify": verify,
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(n, real)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

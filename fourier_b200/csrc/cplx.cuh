@@ -1,0 +1,116 @@
+// cplx.cuh -- complex arithmetic and register-resident butterflies shared by every kernel.
+//
+// Replaces the reference's macro "vector ISA" (fourier-algorithms/src/vector/generic.rs:5-62,
+// vector/avx.rs:6-193) and its butterfly macros (autosort/butterfly.rs:3-65).  Unlike the
+// reference (mul, mul, addsub -- no FMA) the products here are left to contract into FFMA/DFMA;
+// parity with the reference is tolerance-based and FMA only tightens the error.
+//
+// Everything is __host__ __device__ so the same code runs under the CPU emulation used by
+// tests/test_kernel_emulation.py (tools/emulate.cu) -- there is no GPU in the build container.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <type_traits>
+
+#include "twiddle_consts.h"
+
+#define FB_HD __host__ __device__ __forceinline__
+
+namespace fb200 {
+
+template <typename T> struct C2;
+template <> struct C2<float> { using type = float2; };
+template <> struct C2<double> { using type = double2; };
+template <typename T> using cpx = typename C2<T>::type;
+
+template <typename T> FB_HD cpx<T> mk(T re, T im) { cpx<T> r; r.x = re; r.y = im; return r; }
+template <typename V> FB_HD V cadd(V a, V b) { V r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename V> FB_HD V csub(V a, V b) { V r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename V> FB_HD V cmul(V a, V b) {
+  V r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+// a * conj(b)
+template <typename V> FB_HD V cmulc(V a, V b) {
+  V r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+}
+template <typename V, typename T> FB_HD V cscale(V a, T s) { V r; r.x = a.x * s; r.y = a.y * s; return r; }
+template <typename V> FB_HD V cconj(V a) { V r; r.x = a.x; r.y = -a.y; return r; }
+// multiply by -i (forward quarter turn) / +i
+template <typename V> FB_HD V cmul_mi(V a) { V r; r.x = a.y; r.y = -a.x; return r; }
+template <typename V> FB_HD V cmul_pi(V a) { V r; r.x = -a.y; r.y = a.x; return r; }
+// a * w where w is a forward-table twiddle; inverse transforms use the conjugate
+template <bool FWD, typename V> FB_HD V ctw(V a, V w) { return FWD ? cmul(a, w) : cmulc(a, w); }
+
+template <int I, int N, typename F> FB_HD void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+__host__ __device__ constexpr int bitrev(int k, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; ++b) r |= ((k >> b) & 1) << (bits - 1 - b);
+  return r;
+}
+
+// a * w_N^K with w_N = exp(-2*pi*i/N) (FWD) or its conjugate; N | 64, K compile-time.
+template <int N, int K, bool FWD, typename T> FB_HD cpx<T> mul_w(cpx<T> a) {
+  static_assert(64 % N == 0, "compile-time twiddles cover N | 64");
+  constexpr int k = ((K % N) + N) % N;
+  if constexpr (k == 0) {
+    return a;
+  } else if constexpr (4 * k == N) {
+    return FWD ? cmul_mi(a) : cmul_pi(a);
+  } else if constexpr (2 * k == N) {
+    return mk<T>(-a.x, -a.y);
+  } else if constexpr (4 * k == 3 * N) {
+    return FWD ? cmul_pi(a) : cmul_mi(a);
+  } else {
+    constexpr T c = (T)kCos64[k * (64 / N)];
+    constexpr T s = (T)kSin64[k * (64 / N)];  // forward w = (c, -s)
+    constexpr T wy = FWD ? -s : s;
+    return mk<T>(a.x * c - a.y * wy, a.x * wy + a.y * c);
+  }
+}
+
+// In-register radix-2 decimation-in-frequency FFT of x[BASE .. BASE+LEN).  Result is bit-reversed:
+// X[k] ends up in x[BASE + bitrev(k, log2 LEN)].
+template <int LEN, int BASE, bool FWD, typename T, int TOTAL>
+FB_HD void dif2(cpx<T> (&x)[TOTAL]) {
+  if constexpr (LEN >= 2) {
+    constexpr int H = LEN / 2;
+    static_for<0, H>([&](auto J) {
+      constexpr int j = decltype(J)::value;
+      cpx<T> a = x[BASE + j], b = x[BASE + j + H];
+      x[BASE + j] = cadd(a, b);
+      x[BASE + j + H] = mul_w<LEN, j, FWD, T>(csub(a, b));
+    });
+    dif2<H, BASE, FWD, T, TOTAL>(x);
+    dif2<H, BASE + H, FWD, T, TOTAL>(x);
+  }
+}
+
+// DFT of R register values (R in {2,4,8,16,32,64}); X[k] is at x[rev<R>(k)] afterwards.
+template <int R, bool FWD, typename T> FB_HD void dft_pow2(cpx<T> (&x)[R]) { dif2<R, 0, FWD, T, R>(x); }
+template <int R> __host__ __device__ constexpr int rev(int k) { return bitrev(k, ilog2(R)); }
+
+// Radix-3 butterfly, natural order in and out (reference: autosort/butterfly.rs:9-22).
+template <bool FWD, typename T> FB_HD void dft3(cpx<T> (&x)[3]) {
+  constexpr T h = (T)0.86602540378443864676372317075294;  // sqrt(3)/2
+  cpx<T> s = cadd(x[1], x[2]);
+  cpx<T> d = cscale(csub(x[1], x[2]), h);
+  cpx<T> t = mk<T>(x[0].x - (T)0.5 * s.x, x[0].y - (T)0.5 * s.y);
+  cpx<T> r = FWD ? cmul_mi(d) : cmul_pi(d);
+  x[0] = cadd(x[0], s);
+  x[1] = cadd(t, r);
+  x[2] = csub(t, r);
+}
+
+// Scale mode of a Transform code (fourier-algorithms/src/fft.rs:5-16, autosort/mod.rs:381-385).
+enum : int { kFft = 0, kIfft = 1, kUnscaledIfft = 2, kSqrtScaledFft = 3, kSqrtScaledIfft = 4 };
+inline bool transform_is_forward(int code) { return code == kFft || code == kSqrtScaledFft; }
+
+}  // namespace fb200

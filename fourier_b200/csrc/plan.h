@@ -1,0 +1,165 @@
+// plan.h -- host-side plan objects behind the C ABI (include/fourier.h, include/fourier_b200.h).
+//
+// A Plan<T> is what the reference boxes up as `Box<dyn Fft<Real = T> + Send>`
+// (fourier/src/lib.rs:31-60): it owns the twiddle tables and scratch for one transform size and
+// exposes the single required operation, transform_in_place / transform with a Transform code
+// (fourier-algorithms/src/fft.rs:40-82).  Here the tables and scratch live in HBM, the operation
+// is batched, and it is enqueued on a CUDA stream.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cplx.cuh"
+
+namespace fb200 {
+
+// Execution strategy chosen at plan time.
+enum class Path : int {
+  kTrivial = 0,         // N == 1
+  kOnChip = 1,          // one shared-memory Stockham FFT per CTA-slice (pow2 N <= on-chip limit)
+  kTwoPass = 2,         // four-step, two fused kernels, L2-resident intermediate (large pow2 N)
+  kGlobalStages = 3,    // one kernel per Stockham stage over HBM ({2,3}-smooth N, any size)
+  kBluestein = 4,       // chirp-z around a pow2 inner plan, separate kernels
+  kBluesteinFused = 5,  // chirp-z with the inner FFTs on chip, one kernel
+};
+
+const char* path_name(Path p);
+
+// Selection rule of create_fft_f32/f64 (fourier/src/lib.rs:38-42 with autosort/mod.rs:104-117):
+// Autosort iff N = 2^a * 3^b (N >= 1), else Bluestein with inner size next_pow2(2N-1).
+bool is_23_smooth(size_t n);
+size_t bluestein_inner_size(size_t n);  // bluesteins.rs:110
+
+// Grow-only device allocation.
+class DeviceBuffer {
+ public:
+  DeviceBuffer() = default;
+  ~DeviceBuffer();
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  cudaError_t reserve(size_t bytes);
+  void* data() const { return ptr_; }
+  size_t bytes() const { return bytes_; }
+  void release();
+
+ private:
+  void* ptr_ = nullptr;
+  size_t bytes_ = 0;
+};
+
+struct PlanInfo {
+  size_t size = 0;
+  int path = 0;
+  size_t inner_size = 0;     // Bluestein inner FFT length, else 0
+  int inner_path = 0;
+  size_t n1 = 0, n2 = 0;     // two-pass split
+  int precision_bytes = 0;   // 4 or 8
+  int device = 0;
+  size_t table_bytes = 0;    // twiddle / chirp tables resident in HBM
+};
+
+template <typename T>
+class Plan {
+ public:
+  using C = cpx<T>;
+
+  // Returns nullptr (and sets last_error) when the plan cannot be built; size 0 is refused
+  // (the reference never returns for 0: autosort/mod.rs:112).
+  static Plan* create(size_t n, int device, bool allow_fast_paths = true);
+  ~Plan();
+
+  size_t size() const { return n_; }
+  int device() const { return device_; }
+  Path path() const { return path_; }
+  PlanInfo info() const;
+
+  // Batched transform on device-resident data: `batch` contiguous transforms of size() samples,
+  // in == out allowed (in place).  Enqueued on `stream`; not synchronised.
+  cudaError_t exec_device(const C* in, C* out, size_t batch, int code, cudaStream_t stream);
+
+  // Same on host memory (the reference ABI's case): staged H2D -> transform -> D2H through the
+  // plan's own streams, chunked and pipelined; returns after the result is in `out`.
+  cudaError_t exec_host(const C* in, C* out, size_t batch, int code);
+
+  // Number of kernel launches the last exec_* call issued (bench.py reports it).
+  unsigned long long launches() const { return launches_; }
+
+ private:
+  Plan() = default;
+  cudaError_t init(size_t n, int device, bool allow_fast_paths);
+
+  cudaError_t exec_global_stages(const C* in, C* out, size_t batch, int code, cudaStream_t s);
+  cudaError_t exec_onchip(const C* in, C* out, size_t batch, int code, cudaStream_t s);
+  cudaError_t exec_twopass(const C* in, C* out, size_t batch, int code, cudaStream_t s);
+  cudaError_t exec_bluestein(const C* in, C* out, size_t batch, int code, cudaStream_t s);
+  cudaError_t exec_bluestein_fused(const C* in, C* out, size_t batch, int code, cudaStream_t s);
+
+  cudaError_t init_global_stages();
+  cudaError_t init_onchip();
+  cudaError_t init_twopass();
+  cudaError_t init_bluestein(bool allow_fast_paths);
+
+  size_t n_ = 0;
+  int device_ = 0;
+  Path path_ = Path::kTrivial;
+  unsigned long long launches_ = 0;
+
+  // kGlobalStages: radices of the Stockham stages and the full forward table w_N^k, k < N
+  std::vector<int> radices_;
+  DeviceBuffer wtab_;
+
+  // kOnChip / kTwoPass: see onchip.cu / twopass.cu
+  size_t n1_ = 0, n2_ = 0;
+  DeviceBuffer tw_a_, tw_b_;
+
+  // kBluestein*: chirp x[i] (N entries), W = FFT_M(wrapped chirp) (M entries), both forward;
+  // the inverse direction uses their conjugate-symmetric counterparts computed at plan time.
+  size_t m_ = 0;
+  std::unique_ptr<Plan<T>> inner_;
+  DeviceBuffer chirp_, wf_, wi_;
+
+  // scratch (grow-only) and host staging
+  DeviceBuffer work_, work2_;
+  DeviceBuffer stage_[3];
+  cudaStream_t streams_[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t events_[9] = {};
+};
+
+// thread-local error text for the C ABI
+void set_last_error(const std::string& s);
+const char* last_error();
+
+// ---- kernel launchers implemented in the .cu files ------------------------------------------------
+
+// stockham_generic.cu
+template <typename T>
+cudaError_t launch_stockham_stage(int radix, const cpx<T>* in, cpx<T>* out, const cpx<T>* wtab, size_t n,
+                                  size_t sub_size, size_t stride, size_t batch, bool forward, bool last,
+                                  T scale, cudaStream_t s);
+template <typename T>
+cudaError_t launch_scale_copy(const cpx<T>* in, cpx<T>* out, size_t count, T scale, cudaStream_t s);
+template <typename T>
+cudaError_t launch_chirp_in(const cpx<T>* in, cpx<T>* work, const cpx<T>* chirp, size_t n, size_t m,
+                            size_t batch, bool forward, cudaStream_t s);
+template <typename T>
+cudaError_t launch_pointwise(cpx<T>* work, const cpx<T>* w, size_t m, size_t batch, bool forward,
+                             cudaStream_t s);
+template <typename T>
+cudaError_t launch_chirp_out(const cpx<T>* work, cpx<T>* out, const cpx<T>* chirp, size_t n, size_t m,
+                             size_t batch, bool forward, T scale, cudaStream_t s);
+
+// synth.cu: counter-hash synthetic input (same generator as oracle/fourier_oracle.c fo_fill_input_*)
+template <typename T>
+cudaError_t launch_fill_input(T* out, unsigned long long first_scalar, size_t count,
+                              unsigned long long seed, cudaStream_t s);
+
+// host math helpers (plan_math.cpp part of plan.cu)
+void host_twiddle(size_t k, size_t n, double* re, double* im);            // exp(-2*pi*i*k/n), long-double accurate
+void host_fft_pow2(std::vector<double>& re, std::vector<double>& im, bool inverse);  // unscaled, in place
+
+}  // namespace fb200

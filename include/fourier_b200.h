@@ -1,0 +1,90 @@
+/*
+ * fourier_b200.h -- additive entry points of libfourier.so that the reference ABI has no
+ * counterpart for: batched transforms, device-resident buffers, caller-supplied CUDA streams,
+ * device selection and plan introspection.  Nothing here changes the eight reference symbols
+ * declared in fourier.h.
+ *
+ * Why they exist: the reference's hot path is Fft::transform_in_place on ONE transform
+ * (fourier-algorithms/src/fft.rs:48); a GPU needs many independent transforms per call to fill
+ * 148 SMs and HBM, and callers that already hold data on the device must not pay PCIe.  A batch
+ * is `batch` contiguous transforms of size() samples each: transform b occupies samples
+ * [b*size, (b+1)*size).  Every transform of a batch is independent, exactly as if the reference's
+ * transform() were called in a loop (fourier-bench/benches/fft_bench.rs:36).
+ *
+ * All functions return 0 on success and a non-zero cudaError_t value otherwise;
+ * fourier_b200_last_error() returns a description for the calling thread.
+ */
+#ifndef FOURIER_B200_H_
+#define FOURIER_B200_H_
+
+#include "fourier.h"
+
+#ifdef __cplusplus
+extern "C" {
+#define FB200_F ::fourier::c::fourier_fft_float
+#define FB200_D ::fourier::c::fourier_fft_double
+#else
+#define FB200_F struct fourier_fft_float
+#define FB200_D struct fourier_fft_double
+#endif
+#define FB200_PLAN_F const FB200_F
+#define FB200_PLAN_D const FB200_D
+
+/* Device used by plans created afterwards on this thread (default: the current CUDA device). */
+int fourier_b200_set_device(int device);
+int fourier_b200_get_device(void);
+int fourier_b200_device_count(void);
+
+/* Batched Fft::transform (in != out) / Fft::transform_in_place (in == out).  Pointers may be host
+ * memory (pipelined H2D -> transform -> D2H, returns when `out` is complete) or device memory on
+ * the plan's GPU (enqueued on the plan's stream and synchronised before returning). */
+int fourier_b200_transform_batch_float(FB200_PLAN_F *plan, const void *in, void *out, size_t batch,
+                                       int transform);
+int fourier_b200_transform_batch_double(FB200_PLAN_D *plan, const void *in, void *out, size_t batch,
+                                        int transform);
+
+/* Device pointers only; enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) and NOT
+ * synchronised: the call returns as soon as the kernels are queued. */
+int fourier_b200_transform_batch_async_float(FB200_PLAN_F *plan, const void *in_dev, void *out_dev,
+                                             size_t batch, int transform, void *cuda_stream);
+int fourier_b200_transform_batch_async_double(FB200_PLAN_D *plan, const void *in_dev, void *out_dev,
+                                              size_t batch, int transform, void *cuda_stream);
+
+/* Plan introspection (Fft::size, fourier-algorithms/src/fft.rs:45, and the chosen strategy). */
+struct fourier_b200_plan_info {
+  size_t size;        /* transform length N */
+  int path;           /* 0 trivial, 1 onchip, 2 twopass, 3 global_stages, 4 bluestein, 5 bluestein_fused */
+  size_t inner_size;  /* Bluestein inner length next_pow2(2N-1) (bluesteins.rs:110), else 0 */
+  int inner_path;
+  size_t n1, n2;      /* two-pass split N = n1*n2, else 0 */
+  int precision_bytes;
+  int device;
+  size_t table_bytes; /* twiddle / chirp tables resident in HBM */
+  unsigned long long last_launches; /* kernels launched by the most recent transform call */
+};
+int fourier_b200_plan_info_float(FB200_PLAN_F *plan, struct fourier_b200_plan_info *out);
+int fourier_b200_plan_info_double(FB200_PLAN_D *plan, struct fourier_b200_plan_info *out);
+const char *fourier_b200_path_name(int path);
+
+/* Plans restricted to the general one-kernel-per-stage path (testing / comparison). */
+FB200_F *fourier_b200_create_general_float(size_t size);
+FB200_D *fourier_b200_create_general_double(size_t size);
+
+/* Synthetic benchmark input on the device: scalars [first_scalar, first_scalar+count) of the
+ * counter-hash stream with `seed`, uniform in [-1, 1) (re of sample s is scalar 2s, im 2s+1). */
+int fourier_b200_fill_input_float(void *dev_out, unsigned long long first_scalar, size_t count,
+                                  unsigned long long seed, void *cuda_stream);
+int fourier_b200_fill_input_double(void *dev_out, unsigned long long first_scalar, size_t count,
+                                   unsigned long long seed, void *cuda_stream);
+
+const char *fourier_b200_last_error(void);
+const char *fourier_b200_version(void);
+
+#undef FB200_PLAN_F
+#undef FB200_PLAN_D
+#undef FB200_F
+#undef FB200_D
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOURIER_B200_H_ */
