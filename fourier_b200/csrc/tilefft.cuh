@@ -1,0 +1,136 @@
+// tilefft.cuh -- the building block of the fused kernels: a tile of C independent length-L FFTs
+// (L = RA*RB), E samples per thread in registers, ONE shared-memory exchange.
+//
+//   stage A:  n = j + RB*i   DFT_RA over i (registers)  ->  Y[j][p], times w_L^{j*p}
+//   exchange: Y through shared memory (32x32-style transpose per FFT)
+//   stage B:  DFT_RB over j (registers)                 ->  X[p + RA*r]
+//
+// This replaces RA*RB/8.. passes of the reference's stage loop (radix_R_wide / radix_R_narrow,
+// fourier-algorithms/src/autosort/mod.rs:211-284: one full sweep over the array per radix-4/8
+// stage) by a single read and a single write of the tile: for L = 1024 the reference streams the
+// data 4 times (radices 4,8,8,4), here it is loaded once into registers and stored once.
+//
+// Thread <-> data mapping.  TP = L/E threads cooperate on one FFT.  A thread owns NA = E/RA stage-A
+// butterflies (j = u + TP*a) and NB = E/RB stage-B butterflies (p = u + TP*c).  Which of the two
+// tile coordinates runs along the lanes of a warp is chosen per access so that global memory is
+// always touched in >= 64..128-byte contiguous pieces:
+//   "col fast" (CF): lane -> FFT index inside the tile (used when consecutive FFTs are adjacent in
+//                    memory: column tiles of the four-step algorithm)
+//   "u fast"   (UF): lane -> position inside one FFT (used when one FFT is contiguous in memory)
+//
+// Every member is __host__ __device__: tools/emulate.cu runs the identical code thread by thread on
+// the CPU (there is no GPU in the build container), tests/test_kernel_emulation.py checks it.
+#pragma once
+
+#include "cplx.cuh"
+
+namespace fb200 {
+
+// Two consecutive twiddles, loaded with one 128-bit (f32) / two 128-bit (f64) instructions.
+template <typename T> struct alignas(2 * sizeof(cpx<T>)) TwPair { cpx<T> a, b; };
+
+// Table layout for the stage-A twiddles w_L^{j*p}: pair index (p/2)*RB + j holds p even / p odd.
+// Lanes that differ in j read consecutive pairs (UF); lanes that share j broadcast (CF).
+template <int RA, int RB> FB_HD int twa_index(int j, int p_half) { return p_half * RB + j; }
+
+template <typename T, int RA_, int RB_, int E_, int C_, int SJ_, int SP_, int SC_, bool FWD_>
+struct TileFFT {
+  static constexpr int RA = RA_, RB = RB_, E = E_, C = C_;
+  static constexpr int L = RA * RB;
+  static constexpr int TP = L / E;          // threads per FFT
+  static constexpr int NA = E / RA;         // stage-A butterflies per thread
+  static constexpr int NB = E / RB;         // stage-B butterflies per thread
+  static constexpr int THREADS = TP * C;
+  static constexpr int SJ = SJ_, SP = SP_, SC = SC_;  // shared-memory strides of j, p, FFT index
+  static constexpr bool FWD = FWD_;
+  static_assert(E % RA == 0 && E % RB == 0 && L % E == 0, "bad tile shape");
+  static_assert(RB % TP == 0 || TP % RB == 0, "bad tile shape");
+
+  // shared-memory footprint in elements: max index + 1
+  static constexpr int SMEM_ELEMS = (RB - 1) * SJ + (RA - 1) * SP + (C - 1) * SC + 1;
+
+  using V = cpx<T>;
+  V v[E];
+
+  template <bool UF> static FB_HD int col_of(int t) { return UF ? t / TP : t % C; }
+  template <bool UF> static FB_HD int u_of(int t) { return UF ? t % TP : t / C; }
+
+  // global -> registers.  Sample n of FFT `col` lives at base[col*CS + n*NS].
+  template <bool UF, long NS, long CS> FB_HD void load(int t, const V* __restrict__ base) {
+    const int col = col_of<UF>(t), u = u_of<UF>(t);
+    const V* p = base + (long)col * CS + (long)u * NS;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int i = 0; i < RA; ++i) v[a * RA + i] = p[(long)(TP * a + RB * i) * NS];
+  }
+
+  // DFT_RA over i for each owned j, then the stage twiddle w_L^{j*p} (skipped for p == 0).
+  template <bool UF> FB_HD void stage_a(int t, const TwPair<T>* __restrict__ twa) {
+    const int u = u_of<UF>(t);
+    static_for<0, NA>([&](auto A) {
+      constexpr int a = decltype(A)::value;
+      dif2<RA, a * RA, FWD, T, E>(v);
+      const int j = u + TP * a;
+      static_for<0, RA / 2>([&](auto H) {
+        constexpr int h = decltype(H)::value;
+        const TwPair<T> w = twa[twa_index<RA, RB>(j, h)];
+        if constexpr (h != 0) v[a * RA + bitrev(2 * h, ilog2(RA))] = ctw<FWD>(v[a * RA + bitrev(2 * h, ilog2(RA))], w.a);
+        v[a * RA + bitrev(2 * h + 1, ilog2(RA))] = ctw<FWD>(v[a * RA + bitrev(2 * h + 1, ilog2(RA))], w.b);
+      });
+    });
+  }
+
+  // registers -> shared: Y[j][p] of FFT col at smem[j*SJ + p*SP + col*SC]
+  template <bool UF> FB_HD void scatter(int t, V* smem) const {
+    const int col = col_of<UF>(t), u = u_of<UF>(t);
+    static_for<0, NA>([&](auto A) {
+      constexpr int a = decltype(A)::value;
+      V* s = smem + (u + TP * a) * SJ + col * SC;
+      static_for<0, RA>([&](auto P) {
+        constexpr int p = decltype(P)::value;
+        s[p * SP] = v[a * RA + bitrev(p, ilog2(RA))];
+      });
+    });
+  }
+
+  // shared -> registers for stage B: thread owns p = u + TP*c, reads all j
+  template <bool UF> FB_HD void gather(int t, const V* smem) {
+    const int col = col_of<UF>(t), u = u_of<UF>(t);
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+      const V* s = smem + (u + TP * c) * SP + col * SC;
+#pragma unroll
+      for (int j = 0; j < RB; ++j) v[c * RB + j] = s[j * SJ];
+    }
+  }
+
+  FB_HD void stage_b() {
+    static_for<0, NB>([&](auto Cc) {
+      constexpr int c = decltype(Cc)::value;
+      dif2<RB, c * RB, FWD, T, E>(v);
+    });
+  }
+
+  // registers -> global.  Output k = p + RA*r of FFT `col` goes to base[col*CS + k*KS], optionally
+  // multiplied by the inter-pass twiddle tw2[col*CS + k*KS] (same layout as the destination) and by
+  // a real scale factor.
+  template <bool UF, long KS, long CS, bool TW2, bool SCALE>
+  FB_HD void store(int t, V* __restrict__ base, const V* __restrict__ tw2, T scale) const {
+    const int col = col_of<UF>(t), u = u_of<UF>(t);
+    static_for<0, NB>([&](auto Cc) {
+      constexpr int c = decltype(Cc)::value;
+      const long off = (long)col * CS + (long)(u + TP * c) * KS;
+      static_for<0, RB>([&](auto Rr) {
+        constexpr int r = decltype(Rr)::value;
+        V val = v[c * RB + bitrev(r, ilog2(RB))];
+        const long o = off + (long)(RA * r) * KS;
+        if constexpr (TW2) val = ctw<FWD>(val, tw2[o]);
+        if constexpr (SCALE) val = cscale(val, scale);
+        base[o] = val;
+      });
+    });
+  }
+};
+
+}  // namespace fb200
