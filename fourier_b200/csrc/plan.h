@@ -115,7 +115,9 @@ class Plan {
 
   // kOnChip / kTwoPass: see onchip.cu / twopass.cu
   size_t n1_ = 0, n2_ = 0;
-  DeviceBuffer tw_a_, tw_b_;
+  DeviceBuffer tw_a_, tw_b_, tw2_;
+  const void* fast_ops_ = nullptr;   // TwoPassOps<T> / OnChipOps<T> of the selected kernel family
+  size_t chunk_ = 0;                 // transforms per L2-resident chunk (two-pass)
 
   // kBluestein*: chirp x[i] (N entries), W = FFT_M(wrapped chirp) (M entries), both forward;
   // the inverse direction uses their conjugate-symmetric counterparts computed at plan time.

@@ -1,0 +1,168 @@
+// twopass_kernels.cuh -- kernels, per-size configurations and table builders of the two-pass (four-step)
+// path.  Shared by twopass.cu (the product) and tools/emulate.cu (CPU emulation of the same code).
+#pragma once
+
+#include <vector>
+
+#include "plan.h"
+#include "tilefft.cuh"
+
+namespace fb200 {
+namespace twopass {
+
+// ---- kernels ------------------------------------------------------------------------------------------
+// One CTA = one tile of Tile::C FFTs of one transform of the chunk.
+// The body of one tile, split at the CTA barrier so that tools/emulate.cu can run the identical code on
+// the CPU: phase1 for every thread, then phase2 for every thread.
+template <class Tile, long NS, long CS, bool LOAD_UF, long KS, long OCS, bool TW2>
+struct TileBody {
+  using V = typename Tile::V;
+  using T = decltype(V::x);
+  struct Args {
+    const V* in; V* out; const TwPair<T>* twa; const V* tw2;
+    long tile_stride_in, tile_stride_out, batch_stride; int tiles_per_fft; T scale; int do_scale;
+  };
+  static FB_HD void phase1(Tile& f, const Args& a, long block, int t, V* smem) {
+    const int tile = (int)(block % a.tiles_per_fft);
+    const long b = block / a.tiles_per_fft;
+    const V* src = a.in + b * a.batch_stride + (long)tile * a.tile_stride_in;
+    f.template load<LOAD_UF, NS, CS>(t, src);
+    f.template stage_a<LOAD_UF>(t, a.twa);
+    f.template scatter<LOAD_UF>(t, smem);
+  }
+  static FB_HD void phase2(Tile& f, const Args& a, long block, int t, const V* smem) {
+    const int tile = (int)(block % a.tiles_per_fft);
+    const long b = block / a.tiles_per_fft;
+    V* dst = a.out + b * a.batch_stride + (long)tile * a.tile_stride_out;
+    const V* t2 = TW2 ? a.tw2 + (long)tile * a.tile_stride_out : nullptr;
+    f.template gather<false>(t, smem);
+    f.stage_b();
+    if (a.do_scale) f.template store<false, KS, OCS, TW2, true>(t, dst, t2, a.scale);
+    else f.template store<false, KS, OCS, TW2, false>(t, dst, t2, a.scale);
+  }
+};
+
+// One CTA = one tile of Tile::C FFTs of one transform of the chunk.
+template <class Tile, long NS, long CS, bool LOAD_UF, long KS, long OCS, bool TW2, int MINB>
+__global__ void __launch_bounds__(Tile::THREADS, MINB)
+tile_kernel(const typename TileBody<Tile, NS, CS, LOAD_UF, KS, OCS, TW2>::Args a) {
+  using Body = TileBody<Tile, NS, CS, LOAD_UF, KS, OCS, TW2>;
+  using V = typename Tile::V;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* smem = reinterpret_cast<V*>(smem_raw);
+  Tile f;
+  Body::phase1(f, a, blockIdx.x, threadIdx.x, smem);
+  __syncthreads();
+  Body::phase2(f, a, blockIdx.x, threadIdx.x, smem);
+}
+
+template <typename T> struct TwoPassOps {
+  size_t n1, n2;
+  int ra1, rb1, ra2, rb2;
+  cudaError_t (*pass1)(const cpx<T>*, cpx<T>*, const void*, const cpx<T>*, size_t, bool, cudaStream_t);
+  cudaError_t (*pass2)(const cpx<T>*, cpx<T>*, const void*, size_t, bool, T, bool, cudaStream_t);
+  cudaError_t (*prepare)();
+};
+
+// Configuration of one supported size: both passes use R x R register stages.
+template <typename T, int R1, int R2, int C1, int C2, int PAD1, int MINB1, int MINB2>
+struct TwoPass {
+  static constexpr long N1 = (long)R1 * R1, N2 = (long)R2 * R2, N = N1 * N2;
+  // pass 1: FFT length N1 over n1 (stride N2), C1 adjacent columns; both stages "col fast"
+  template <bool FWD> using Tile1 = TileFFT<T, R1, R1, R1, C1, R1 * C1 + PAD1, C1, 1, FWD>;
+  // pass 2: FFT length N2 over contiguous rows, C2 adjacent rows; stage A "u fast", stage B "col fast"
+  template <bool FWD> using Tile2 = TileFFT<T, R2, R2, R2, C2, R2 * C2 + 1, C2, 1, FWD>;
+  template <bool FWD> using Body1 = TileBody<Tile1<FWD>, N2, 1, false, N2, 1, true>;
+  template <bool FWD> using Body2 = TileBody<Tile2<FWD>, 1, N2, true, N1, 1, false>;
+  template <bool FWD> static constexpr auto k1() {
+    return &tile_kernel<Tile1<FWD>, N2, 1, false, N2, 1, true, MINB1>;
+  }
+  template <bool FWD> static constexpr auto k2() {
+    return &tile_kernel<Tile2<FWD>, 1, N2, true, N1, 1, false, MINB2>;
+  }
+  template <bool FWD>
+  static typename Body1<FWD>::Args args1(const cpx<T>* in, cpx<T>* scratch, const void* twa, const cpx<T>* tw2) {
+    return {in, scratch, (const TwPair<T>*)twa, tw2, C1, C1, N, (int)(N2 / C1), (T)1, 0};
+  }
+  template <bool FWD>
+  static typename Body2<FWD>::Args args2(const cpx<T>* scratch, cpx<T>* out, const void* twa, T scale,
+                                         bool do_scale) {
+    return {scratch, out, (const TwPair<T>*)twa, nullptr, (long)C2 * N2, C2, N, (int)(N1 / C2), scale,
+            do_scale ? 1 : 0};
+  }
+  static constexpr size_t smem1 = sizeof(cpx<T>) * Tile1<true>::SMEM_ELEMS;
+  static constexpr size_t smem2 = sizeof(cpx<T>) * Tile2<true>::SMEM_ELEMS;
+
+  static cudaError_t prepare() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k1<true>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1))) return e;
+    if ((e = cudaFuncSetAttribute(k1<false>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1))) return e;
+    if ((e = cudaFuncSetAttribute(k2<true>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2))) return e;
+    if ((e = cudaFuncSetAttribute(k2<false>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2))) return e;
+    return cudaSuccess;
+  }
+  static cudaError_t pass1(const cpx<T>* in, cpx<T>* scratch, const void* twa, const cpx<T>* tw2, size_t nb,
+                           bool fwd, cudaStream_t s) {
+    const unsigned grid = (unsigned)(nb * (N2 / C1));
+    if (fwd) k1<true>()<<<grid, Tile1<true>::THREADS, smem1, s>>>(args1<true>(in, scratch, twa, tw2));
+    else k1<false>()<<<grid, Tile1<true>::THREADS, smem1, s>>>(args1<false>(in, scratch, twa, tw2));
+    return cudaGetLastError();
+  }
+  static cudaError_t pass2(const cpx<T>* scratch, cpx<T>* out, const void* twa, size_t nb, bool fwd, T scale,
+                           bool do_scale, cudaStream_t s) {
+    const unsigned grid = (unsigned)(nb * (N1 / C2));
+    if (fwd) k2<true>()<<<grid, Tile2<true>::THREADS, smem2, s>>>(args2<true>(scratch, out, twa, scale, do_scale));
+    else k2<false>()<<<grid, Tile2<true>::THREADS, smem2, s>>>(args2<false>(scratch, out, twa, scale, do_scale));
+    return cudaGetLastError();
+  }
+  static const TwoPassOps<T>* ops() {
+    static const TwoPassOps<T> o = {(size_t)N1, (size_t)N2, R1, R1, R2, R2, &pass1, &pass2, &prepare};
+    return &o;
+  }
+};
+
+// Supported sizes.  f32: 32x32 register stages (1024-point tiles); f64: 16x16 (256-point tiles).
+template <typename T> const TwoPassOps<T>* lookup(size_t n);
+template <> inline const TwoPassOps<float>* lookup<float>(size_t n) {
+  switch (n) {
+    case (size_t)1 << 20: return TwoPass<float, 32, 32, 8, 8, 8, 2, 2>::ops();
+    case (size_t)1 << 16: return TwoPass<float, 16, 16, 16, 16, 0, 2, 2>::ops();
+    case (size_t)1 << 18: return TwoPass<float, 16, 32, 16, 8, 0, 2, 2>::ops();
+    default: return nullptr;
+  }
+}
+template <> inline const TwoPassOps<double>* lookup<double>(size_t n) {
+  switch (n) {
+    case (size_t)1 << 16: return TwoPass<double, 16, 16, 8, 8, 4, 2, 2>::ops();
+    case (size_t)1 << 12: return TwoPass<double, 8, 8, 16, 16, 0, 4, 4>::ops();
+    case (size_t)1 << 14: return TwoPass<double, 8, 16, 16, 8, 0, 4, 2>::ops();
+    default: return nullptr;
+  }
+}
+
+// Stage-A twiddle table of a length-L = RA*RB tile: pair (h, j) = (w_L^{j*2h}, w_L^{j*(2h+1)}).
+template <typename T>
+std::vector<TwPair<T>> make_twa(int ra, int rb) {
+  const size_t L = (size_t)ra * rb;
+  std::vector<TwPair<T>> t((size_t)(ra / 2) * rb);
+  for (int h = 0; h < ra / 2; ++h)
+    for (int j = 0; j < rb; ++j) {
+      double re, im;
+      TwPair<T> p;
+      host_twiddle((size_t)j * (2 * h), L, &re, &im); p.a = mk<T>((T)re, (T)im);
+      host_twiddle((size_t)j * (2 * h + 1), L, &re, &im); p.b = mk<T>((T)re, (T)im);
+      t[(size_t)h * rb + j] = p;
+    }
+  return t;
+}
+
+template <typename T, typename U>
+cudaError_t upload_vec(DeviceBuffer& buf, const std::vector<U>& host) {
+  cudaError_t e = buf.reserve(host.size() * sizeof(U));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(buf.data(), host.data(), host.size() * sizeof(U), cudaMemcpyHostToDevice);
+}
+
+
+}  // namespace twopass
+}  // namespace fb200

@@ -1,0 +1,157 @@
+// emulate.cu -- runs the fused kernels' device code on the CPU, thread by thread and phase by phase
+// (the code in tilefft.cuh / twopass_kernels.cuh is __host__ __device__), and checks the result
+// against a double-precision FFT.  There is no GPU in the build container, so this is how index maps,
+// twiddle tables and shared-memory layouts are verified before a kernel ever runs on the B200.
+// It also reports shared-memory bank conflicts of the exchange (64-bit/128-bit access model).
+// Build: nvcc -std=c++17 -O1 --expt-relaxed-constexpr -I fourier_b200/csrc tools/emulate.cu \
+//             fourier_b200/csrc/plan.cu ... (host only, never run on the device)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "twopass_kernels.cuh"
+
+using namespace fb200;
+using namespace fb200::twopass;
+
+template <typename T> static void fill(std::vector<cpx<T>>& x, unsigned seed) {
+  unsigned long long s = seed * 2654435761ull + 12345;
+  for (auto& v : x) {
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    v.x = (T)((double)(s >> 11) / 9007199254740992.0 * 2 - 1);
+    s = s * 6364136223846793005ull + 1442695040888963407ull;
+    v.y = (T)((double)(s >> 11) / 9007199254740992.0 * 2 - 1);
+  }
+}
+
+// worst-case bank conflict degree of one warp-wide shared access, element size B bytes:
+// lanes are served in groups of 128 bytes worth of lanes (half-warp for 8 B, quarter-warp for 16 B)
+template <int B> static int conflict_degree(const std::vector<long>& elem_index) {
+  const int group = 128 / B;
+  int worst = 1;
+  for (size_t g = 0; g + group <= elem_index.size(); g += group) {
+    int count[32] = {0};
+    // distinct addresses in the same bank conflict; identical addresses broadcast
+    std::vector<long> seen;
+    for (int l = 0; l < group; ++l) {
+      long e = elem_index[g + l];
+      bool dup = false;
+      for (long s : seen) dup |= (s == e);
+      if (dup) continue;
+      seen.push_back(e);
+      int bank = (int)((e * B / 4) % 32);
+      worst = std::max(worst, ++count[bank]);
+    }
+  }
+  return worst;
+}
+
+// Runs one tile body (both phases) for `blocks` CTAs on the CPU.
+template <class Body, class Tile>
+static void run_body(const typename Body::Args& a, long blocks) {
+  using V = typename Tile::V;
+  std::vector<V> smem(Tile::SMEM_ELEMS);
+  std::vector<Tile> thr(Tile::THREADS);
+  for (long b = 0; b < blocks; ++b) {
+    for (int t = 0; t < Tile::THREADS; ++t) Body::phase1(thr[t], a, b, t, smem.data());
+    for (int t = 0; t < Tile::THREADS; ++t) Body::phase2(thr[t], a, b, t, smem.data());
+  }
+}
+
+// Bank-conflict report for the exchange of a tile: scatter with mapping UF_A, gather with col-fast.
+template <class Tile, bool UF_A>
+static void report_conflicts(const char* name) {
+  using V = typename Tile::V;
+  constexpr int B = (int)sizeof(V);
+  int worst_w = 1, worst_r = 1;
+  for (int warp = 0; warp < Tile::THREADS / 32; ++warp) {
+    for (int a = 0; a < Tile::NA; ++a)
+      for (int p = 0; p < Tile::RA; ++p) {
+        std::vector<long> idx;
+        for (int l = 0; l < 32; ++l) {
+          const int t = warp * 32 + l;
+          idx.push_back((long)(Tile::template u_of<UF_A>(t) + Tile::TP * a) * Tile::SJ + (long)p * Tile::SP +
+                        (long)Tile::template col_of<UF_A>(t) * Tile::SC);
+        }
+        worst_w = std::max(worst_w, conflict_degree<B>(idx));
+      }
+    for (int c = 0; c < Tile::NB; ++c)
+      for (int j = 0; j < Tile::RB; ++j) {
+        std::vector<long> idx;
+        for (int l = 0; l < 32; ++l) {
+          const int t = warp * 32 + l;
+          idx.push_back((long)j * Tile::SJ + (long)(Tile::template u_of<false>(t) + Tile::TP * c) * Tile::SP +
+                        (long)Tile::template col_of<false>(t) * Tile::SC);
+        }
+        worst_r = std::max(worst_r, conflict_degree<B>(idx));
+      }
+  }
+  printf("  %-8s threads %4d smem %6zu B  exchange conflicts: write x%d, read x%d\n", name, Tile::THREADS,
+         sizeof(V) * Tile::SMEM_ELEMS, worst_w, worst_r);
+}
+
+template <typename T, class Cfg>
+static int check(const char* name, double tol) {
+  const long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
+  const int batch = 2;
+  printf("%s: N=%ld = %ld x %ld\n", name, N, N1, N2);
+  report_conflicts<typename Cfg::template Tile1<true>, false>("pass 1");
+  report_conflicts<typename Cfg::template Tile2<true>, true>("pass 2");
+  int bad = 0;
+  for (int fwd = 1; fwd >= 0; --fwd) {
+    std::vector<cpx<T>> x((size_t)N * batch), scratch((size_t)N * batch), out((size_t)N * batch);
+    fill<T>(x, 7 + fwd);
+    const auto* ops = Cfg::ops();
+    auto twa1 = make_twa<T>(ops->ra1, ops->rb1), twa2 = make_twa<T>(ops->ra2, ops->rb2);
+    std::vector<cpx<T>> tw2(N);
+    for (long k1 = 0; k1 < N1; ++k1)
+      for (long c = 0; c < N2; ++c) {
+        double re, im;
+        host_twiddle((size_t)(k1 * c), (size_t)N, &re, &im);
+        tw2[k1 * N2 + c] = mk<T>((T)re, (T)im);
+      }
+    const T scale = (T)0.5;
+    if (fwd) {
+      run_body<typename Cfg::template Body1<true>, typename Cfg::template Tile1<true>>(
+          Cfg::template args1<true>(x.data(), scratch.data(), twa1.data(), tw2.data()), batch * (N2 / Cfg::template Tile1<true>::C));
+      run_body<typename Cfg::template Body2<true>, typename Cfg::template Tile2<true>>(
+          Cfg::template args2<true>(scratch.data(), out.data(), twa2.data(), scale, true), batch * (N1 / Cfg::template Tile2<true>::C));
+    } else {
+      run_body<typename Cfg::template Body1<false>, typename Cfg::template Tile1<false>>(
+          Cfg::template args1<false>(x.data(), scratch.data(), twa1.data(), tw2.data()), batch * (N2 / Cfg::template Tile1<false>::C));
+      run_body<typename Cfg::template Body2<false>, typename Cfg::template Tile2<false>>(
+          Cfg::template args2<false>(scratch.data(), out.data(), twa2.data(), scale, true), batch * (N1 / Cfg::template Tile2<false>::C));
+    }
+    double worst = 0;
+    for (int b = 0; b < batch; ++b) {
+      std::vector<double> re(N), im(N);
+      for (long i = 0; i < N; ++i) { re[i] = x[(size_t)b * N + i].x; im[i] = x[(size_t)b * N + i].y; }
+      host_fft_pow2(re, im, !fwd);
+      double maxref = 0, maxerr = 0;
+      for (long i = 0; i < N; ++i) {
+        const double rr = re[i] * 0.5, ii = im[i] * 0.5;
+        maxref = std::max(maxref, std::hypot(rr, ii));
+        maxerr = std::max(maxerr, std::hypot(out[(size_t)b * N + i].x - rr, out[(size_t)b * N + i].y - ii));
+      }
+      worst = std::max(worst, maxerr / maxref);
+    }
+    printf("  %s: max rel err vs f64 FFT %.3e (tol %.1e) %s\n", fwd ? "forward" : "inverse", worst, tol,
+           worst < tol ? "OK" : "FAIL");
+    bad += !(worst < tol);
+  }
+  return bad;
+}
+
+int main() {
+  int bad = 0;
+  bad += check<float, TwoPass<float, 32, 32, 8, 8, 8, 2, 2>>("f32 2^20 (C=8)", 2e-6);
+  bad += check<float, TwoPass<float, 32, 32, 16, 16, 0, 1, 1>>("f32 2^20 (C=16)", 2e-6);
+  bad += check<float, TwoPass<float, 16, 16, 16, 16, 0, 2, 2>>("f32 2^16", 2e-6);
+  bad += check<float, TwoPass<float, 16, 32, 16, 8, 0, 2, 2>>("f32 2^18", 2e-6);
+  bad += check<double, TwoPass<double, 16, 16, 8, 8, 4, 2, 2>>("f64 2^16", 5e-15);
+  bad += check<double, TwoPass<double, 8, 8, 16, 16, 0, 4, 4>>("f64 2^12", 5e-15);
+  bad += check<double, TwoPass<double, 8, 16, 16, 8, 0, 4, 2>>("f64 2^14", 5e-15);
+  printf(bad ? "EMULATION FAILED (%d)\n" : "EMULATION OK\n", bad);
+  return bad ? 1 : 0;
+}
