@@ -1,0 +1,309 @@
+// fused_kernels.cuh -- the flagship kernel: both passes of the four-step FFT in ONE persistent,
+// warp-specialised launch.
+//
+//   * one CTA per SM, G groups of threads, each processing one TileFFT tile in registers at a time;
+//   * thread 0 of a group is its producer: it claims items of a global work queue (atomic counter)
+//     whose order interleaves pass-1 tiles of transform s with pass-2 tiles of transform s-LAG,
+//     probes the tile's dependencies, and brings the tile into the group's shared-memory staging
+//     buffer with TMA: a 2-D tensor-map box for the
+//     strided column tiles of pass 1 (cp.async.bulk.tensor), plain bulk copies for the contiguous
+//     row tiles of pass 2 (cp.async.bulk) -- completion is signalled on an mbarrier (full[g]);
+//   * a consumer group waits on full[g], pulls its 32 (16) samples per thread out of the staging
+//     buffer, releases it (empty[g]) so the next tile's TMA overlaps ALL of the remaining work,
+//     runs stage A, exchanges through a shared buffer (one buffer, taken under a lock: the
+//     exchange is ~10% of a tile), runs stage B and stores straight from registers;
+//   * the intermediate A[k1][n2] lives in a ring of RING transforms (a few tens of MB) that stays
+//     in the 126 MB L2: pass-1 tiles of transform b may only start once pass 2 of transform b-RING
+//     has consumed the slot (done2), pass-2 tiles of b once all pass-1 tiles of b are stored (done1).
+//     Every dependency points to an earlier queue position, so the scheme cannot deadlock.
+//
+// HBM therefore sees each sample exactly twice (one read, one write); there are no launch gaps or
+// partial waves, and memory latency is hidden by the TMA prefetch instead of by occupancy.
+#pragma once
+
+#include <cuda.h>
+
+#include <cstdint>
+
+#include "tilefft.cuh"
+
+namespace fb200 {
+namespace fused {
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug must abort the kernel (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (unsigned spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 22)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned target) {
+  for (unsigned spins = 0; ld_acquire(p) < target; ++spins) {
+    if (spins > (1u << 24)) __trap();
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ void group_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---- work queue ---------------------------------------------------------------------------------------------
+struct WorkItem { int pass, b, tile; };  // pass: 1, 2, or -1 = queue exhausted
+
+// Queue order: slot s = 0 .. B+LAG-1 holds [pass-1 tiles of transform s] then [pass-2 tiles of s-LAG].
+__host__ __device__ inline WorkItem decode_work(long w, int batch, int lag, int t1, int t2) {
+  WorkItem it = {-1, 0, 0};
+  const long total = (long)batch * (t1 + t2);
+  if (w >= total) return it;
+  const int d = lag < batch ? lag : batch;
+  const long pro = (long)d * t1;
+  if (w < pro) { it.pass = 1; it.b = (int)(w / t1); it.tile = (int)(w % t1); return it; }
+  w -= pro;
+  const long steady = (long)(batch - d) * (t1 + t2);
+  if (w < steady) {
+    const int s = d + (int)(w / (t1 + t2));
+    const int r = (int)(w % (t1 + t2));
+    if (r < t1) { it.pass = 1; it.b = s; it.tile = r; }
+    else { it.pass = 2; it.b = s - d; it.tile = r - t1; }
+    return it;
+  }
+  w -= steady;
+  it.pass = 2; it.b = (batch - d) + (int)(w / t2); it.tile = (int)(w % t2);
+  return it;
+}
+
+template <typename T> struct FusedArgs {
+  const cpx<T>* in;
+  cpx<T>* out;
+  cpx<T>* scratch;            // RING transforms
+  const TwPair<T>* twa1;
+  const TwPair<T>* twa2;
+  const cpx<T>* tw2;          // inter-pass twiddles, layout of the intermediate
+  unsigned* counters;         // [0] queue head, [1 .. 1+B) done1, [1+B .. 1+2B) done2
+  int batch, ring, lag;
+  T scale;
+  int do_scale;
+};
+
+// Configuration: N = (R*R)^2, tiles of C FFTs, G consumer groups per CTA.
+template <typename T_, int R_, int C_, int G_, int PAD1_>
+struct FusedCfg {
+  using T = T_;
+  static constexpr int R = R_, C = C_, G = G_;
+  static constexpr long L = (long)R * R, N1 = L, N2 = L, N = N1 * N2;
+  template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
+  using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
+  using Lay2 = ExLayout<R * C + 1, C, 1>;                          // pass 2: scatter u-fast, gather col-fast
+  static constexpr int GT = R * C;                    // threads per consumer group
+  static constexpr int CONSUMERS = G * GT;
+  static constexpr int THREADS = CONSUMERS;           // thread 0 of each group doubles as its TMA producer
+  static constexpr int T1 = (int)(N2 / C), T2 = (int)(N1 / C);
+  static constexpr uint32_t TILE_BYTES = (uint32_t)(sizeof(cpx<T>) * C * L);
+  static constexpr int EX1 = Tile<true>::template smem_elems<Lay1>(), EX2 = Tile<true>::template smem_elems<Lay2>();
+  static constexpr int EX_ELEMS = EX1 > EX2 ? EX1 : EX2;
+  static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * EX_ELEMS + 127) / 128) * 128;
+  static constexpr size_t SMEM_BYTES = (size_t)G * TILE_BYTES + EX_BYTES + 256 + 1024 /*alignment slack*/;
+  static constexpr int BOX_ROWS = L < 256 ? (int)L : 256;   // TMA box limit: 256 per dimension
+};
+
+// Issues the loads of one work item into staging buffer `dst` (called by one thread of the group).
+template <class Cfg>
+__device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap* in_map,
+                                           const FusedArgs<typename Cfg::T>& a, cpx<typename Cfg::T>* dst,
+                                           uint64_t* full, WorkItem* desc) {
+  using V = cpx<typename Cfg::T>;
+  constexpr int C = Cfg::C;
+  *desc = wi;
+  if (wi.pass < 0) { mbar_arrive(full); return; }
+  fence_proxy_async();   // the group's generic-proxy reads of `dst` precede the async-proxy refill
+  mbar_arrive_expect_tx(full, Cfg::TILE_BYTES);
+  if (wi.pass == 1) {
+    constexpr int BOX = Cfg::BOX_ROWS;
+    const int x = wi.tile * C * 2;  // in scalars of T
+#pragma unroll
+    for (int r0 = 0; r0 < (int)Cfg::L; r0 += BOX)
+      tma_load_2d(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), full);
+  } else {
+    const V* src = a.scratch + (size_t)(wi.b % a.ring) * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
+    constexpr uint32_t PIECE = 16384;
+#pragma unroll
+    for (uint32_t o = 0; o < Cfg::TILE_BYTES; o += PIECE)
+      bulk_load((unsigned char*)dst + o, (const unsigned char*)src + o,
+                Cfg::TILE_BYTES - o < PIECE ? Cfg::TILE_BYTES - o : PIECE, full);
+  }
+}
+
+// Dependencies of a work item: returns true when they are satisfied (non-blocking probe).
+template <class Cfg>
+__device__ __forceinline__ bool deps_ready(const WorkItem& wi, const FusedArgs<typename Cfg::T>& a) {
+  const unsigned* done1 = a.counters + 1;
+  const unsigned* done2 = a.counters + 1 + a.batch;
+  if (wi.pass == 1 && wi.b >= a.ring) return ld_acquire(&done2[wi.b - a.ring]) >= (unsigned)Cfg::T2;
+  if (wi.pass == 2) return ld_acquire(&done1[wi.b]) >= (unsigned)Cfg::T1;
+  return true;
+}
+template <class Cfg>
+__device__ __forceinline__ void deps_wait(const WorkItem& wi, const FusedArgs<typename Cfg::T>& a) {
+  for (unsigned spins = 0; !deps_ready<Cfg>(wi, a); ++spins) {
+    if (spins > (1u << 24)) __trap();
+    __nanosleep(100);
+  }
+}
+
+template <class Cfg, bool FWD>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs<typename Cfg::T> a) {
+  using T = typename Cfg::T;
+  using V = cpx<T>;
+  constexpr int G = Cfg::G, GT = Cfg::GT, C = Cfg::C;
+  constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2, L = Cfg::L;
+  constexpr int T1 = Cfg::T1, T2 = Cfg::T2;
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  V* staging = reinterpret_cast<V*>(base);                                        // [G][C*L]
+  V* exch = reinterpret_cast<V*>(base + (size_t)G * Cfg::TILE_BYTES);
+  unsigned char* ctl = base + (size_t)G * Cfg::TILE_BYTES + Cfg::EX_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctl);            // [G] TMA landed
+  uint64_t* empty = full + G;                                   // [G] staging consumed by the whole group
+  WorkItem* desc = reinterpret_cast<WorkItem*>(empty + G);      // [G]
+  int* lock = reinterpret_cast<int*>(desc + G);
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int g = 0; g < G; ++g) { mbar_init(&full[g], 1); mbar_init(&empty[g], GT); }
+    *lock = 0;
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  unsigned* queue = a.counters;
+  unsigned* done1 = a.counters + 1;
+  unsigned* done2 = a.counters + 1 + a.batch;
+
+  const int g = tid / GT;
+  const int t = tid - g * GT;
+  V* stage_g = staging + (size_t)g * C * L;
+  const int bar_id = 1 + g;
+  using Tile = typename Cfg::template Tile<FWD>;
+  using Lay1 = typename Cfg::Lay1;
+  using Lay2 = typename Cfg::Lay2;
+
+  // Thread 0 of each group is the group's producer: it claims queue items one ahead (`nxt`), and
+  // issues the TMA for the next tile as soon as the current one has left the staging buffer.
+  WorkItem nxt = {-1, 0, 0};
+  bool exhausted = false;
+  if (t == 0) {
+    WorkItem first = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+    deps_wait<Cfg>(first, a);
+    issue_tile<Cfg>(first, &in_map, a, stage_g, &full[g], &desc[g]);
+    exhausted = first.pass < 0;
+    if (!exhausted) nxt = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+  }
+
+  for (uint32_t k = 0;; ++k) {
+    mbar_wait(&full[g], k & 1);
+    const WorkItem wi = desc[g];
+    if (wi.pass < 0) break;
+    bool pending = false;
+
+    // ---- phase 1: staging -> registers, stage A, then hand the staging buffer back ----------------------
+    Tile f;
+    if (wi.pass == 1) {
+      f.template load<false, C, 1>(t, stage_g);        // staging = [n1][C]
+      f.template stage_a<false>(t, a.twa1);
+    } else {
+      f.template load<true, 1, N2>(t, stage_g);        // staging = C contiguous rows
+      f.template stage_a<true>(t, a.twa2);
+    }
+    mbar_arrive(&empty[g]);
+    if (t == 0) {
+      mbar_wait(&empty[g], k & 1);                     // every thread of the group has its samples
+      if (wi.pass == 2) red_release_add(&done2[wi.b], 1u);   // ring slot consumed by this tile
+      if (!exhausted) {
+        if (deps_ready<Cfg>(nxt, a)) {
+          issue_tile<Cfg>(nxt, &in_map, a, stage_g, &full[g], &desc[g]);
+          exhausted = nxt.pass < 0;
+          if (!exhausted) nxt = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+        } else {
+          pending = true;                              // never block here: our own tile may be the dependency
+        }
+      }
+      unsigned spins = 0;
+      while (atomicCAS(lock, 0, 1) != 0) if (++spins > (1u << 26)) __trap();
+    }
+    // ---- phase 2: exchange through the shared buffer (held under the lock) ---------------------------------
+    group_sync(bar_id, GT);
+    if (wi.pass == 1) f.template scatter<false, Lay1>(t, exch); else f.template scatter<true, Lay2>(t, exch);
+    group_sync(bar_id, GT);
+    if (wi.pass == 1) f.template gather<false, Lay1>(t, exch); else f.template gather<false, Lay2>(t, exch);
+    group_sync(bar_id, GT);
+    if (t == 0) { __threadfence_block(); atomicExch(lock, 0); }
+    // ---- phase 3: stage B and the stores --------------------------------------------------------------------
+    if (wi.pass == 1) {
+      f.stage_b();
+      V* dst = a.scratch + (size_t)(wi.b % a.ring) * N + (size_t)wi.tile * C;
+      f.template store<false, N2, 1, true, false>(t, dst, a.tw2 + (size_t)wi.tile * C, (T)1);
+      group_sync(bar_id, GT);
+      if (t == 0) { __threadfence(); red_release_add(&done1[wi.b], 1u); }
+    } else {
+      f.stage_b();
+      V* dst = a.out + (size_t)wi.b * N + (size_t)wi.tile * C;
+      if (a.do_scale) f.template store<false, N1, 1, false, true>(t, dst, nullptr, a.scale);
+      else f.template store<false, N1, 1, false, false>(t, dst, nullptr, a.scale);
+    }
+    if (t == 0 && pending) {
+      deps_wait<Cfg>(nxt, a);
+      issue_tile<Cfg>(nxt, &in_map, a, stage_g, &full[g], &desc[g]);
+      exhausted = nxt.pass < 0;
+      if (!exhausted) nxt = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+    }
+  }
+}
+
+}  // namespace fused
+}  // namespace fb200

@@ -118,6 +118,9 @@ class Plan {
   DeviceBuffer tw_a_, tw_b_, tw2_;
   const void* fast_ops_ = nullptr;   // TwoPassOps<T> / OnChipOps<T> of the selected kernel family
   size_t chunk_ = 0;                 // transforms per L2-resident chunk (two-pass)
+  const void* fused_ops_ = nullptr;  // FusedOps<T>: persistent single-launch variant
+  int ring_ = 0, lag_ = 0, sm_count_ = 148;
+  DeviceBuffer counters_;
 
   // kBluestein*: chirp x[i] (N entries), W = FFT_M(wrapped chirp) (M entries), both forward;
   // the inverse direction uses their conjugate-symmetric counterparts computed at plan time.

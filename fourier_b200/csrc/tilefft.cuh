@@ -33,7 +33,13 @@ template <typename T> struct alignas(2 * sizeof(cpx<T>)) TwPair { cpx<T> a, b; }
 // Lanes that differ in j read consecutive pairs (UF); lanes that share j broadcast (CF).
 template <int RA, int RB> FB_HD int twa_index(int j, int p_half) { return p_half * RB + j; }
 
-template <typename T, int RA_, int RB_, int E_, int C_, int SJ_, int SP_, int SC_, bool FWD_>
+// Shared-memory layout of the exchange: Y[j][p] of FFT `col` at j*SJ + p*SP + col*SC (in elements).
+template <int SJ_, int SP_, int SC_> struct ExLayout {
+  static constexpr int SJ = SJ_, SP = SP_, SC = SC_;
+  template <int RA, int RB, int C> static constexpr int elems() { return (RB - 1) * SJ + (RA - 1) * SP + (C - 1) * SC + 1; }
+};
+
+template <typename T, int RA_, int RB_, int E_, int C_, bool FWD_>
 struct TileFFT {
   static constexpr int RA = RA_, RB = RB_, E = E_, C = C_;
   static constexpr int L = RA * RB;
@@ -41,13 +47,12 @@ struct TileFFT {
   static constexpr int NA = E / RA;         // stage-A butterflies per thread
   static constexpr int NB = E / RB;         // stage-B butterflies per thread
   static constexpr int THREADS = TP * C;
-  static constexpr int SJ = SJ_, SP = SP_, SC = SC_;  // shared-memory strides of j, p, FFT index
   static constexpr bool FWD = FWD_;
   static_assert(E % RA == 0 && E % RB == 0 && L % E == 0, "bad tile shape");
   static_assert(RB % TP == 0 || TP % RB == 0, "bad tile shape");
 
-  // shared-memory footprint in elements: max index + 1
-  static constexpr int SMEM_ELEMS = (RB - 1) * SJ + (RA - 1) * SP + (C - 1) * SC + 1;
+  // shared-memory footprint of the exchange in elements for layout LAY
+  template <class LAY> static constexpr int smem_elems() { return LAY::template elems<RA, RB, C>(); }
 
   using V = cpx<T>;
   V v[E];
@@ -81,8 +86,9 @@ struct TileFFT {
     });
   }
 
-  // registers -> shared: Y[j][p] of FFT col at smem[j*SJ + p*SP + col*SC]
-  template <bool UF> FB_HD void scatter(int t, V* smem) const {
+  // registers -> shared (layout LAY)
+  template <bool UF, class LAY> FB_HD void scatter(int t, V* smem) const {
+    constexpr int SJ = LAY::SJ, SP = LAY::SP, SC = LAY::SC;
     const int col = col_of<UF>(t), u = u_of<UF>(t);
     static_for<0, NA>([&](auto A) {
       constexpr int a = decltype(A)::value;
@@ -95,7 +101,8 @@ struct TileFFT {
   }
 
   // shared -> registers for stage B: thread owns p = u + TP*c, reads all j
-  template <bool UF> FB_HD void gather(int t, const V* smem) {
+  template <bool UF, class LAY> FB_HD void gather(int t, const V* smem) {
+    constexpr int SJ = LAY::SJ, SP = LAY::SP, SC = LAY::SC;
     const int col = col_of<UF>(t), u = u_of<UF>(t);
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
@@ -121,14 +128,39 @@ struct TileFFT {
     static_for<0, NB>([&](auto Cc) {
       constexpr int c = decltype(Cc)::value;
       const long off = (long)col * CS + (long)(u + TP * c) * KS;
-      static_for<0, RB>([&](auto Rr) {
-        constexpr int r = decltype(Rr)::value;
-        V val = v[c * RB + bitrev(r, ilog2(RB))];
-        const long o = off + (long)(RA * r) * KS;
-        if constexpr (TW2) val = ctw<FWD>(val, tw2[o]);
-        if constexpr (SCALE) val = cscale(val, scale);
-        base[o] = val;
-      });
+      if constexpr (TW2) {
+        // Inter-pass twiddles come from L2: fetch them in batches of TWB so that a batch costs one
+        // round trip instead of one per value (the values of a batch are all loaded before first use).
+        constexpr int TWB = RB < 8 ? RB : 8;
+        V w[TWB];
+#pragma unroll
+        for (int q = 0; q < TWB; ++q) w[q] = tw2[off + (long)(RA * q) * KS];
+        static_for<0, RB / TWB>([&](auto G) {
+          constexpr int g = decltype(G)::value;
+          V wn[TWB];
+          if constexpr ((g + 1) * TWB < RB) {
+#pragma unroll
+            for (int q = 0; q < TWB; ++q) wn[q] = tw2[off + (long)(RA * ((g + 1) * TWB + q)) * KS];
+          }
+          static_for<0, TWB>([&](auto Q) {
+            constexpr int r = g * TWB + decltype(Q)::value;
+            V val = ctw<FWD>(v[c * RB + bitrev(r, ilog2(RB))], w[decltype(Q)::value]);
+            if constexpr (SCALE) val = cscale(val, scale);
+            base[off + (long)(RA * r) * KS] = val;
+          });
+          if constexpr ((g + 1) * TWB < RB) {
+#pragma unroll
+            for (int q = 0; q < TWB; ++q) w[q] = wn[q];
+          }
+        });
+      } else {
+        static_for<0, RB>([&](auto Rr) {
+          constexpr int r = decltype(Rr)::value;
+          V val = v[c * RB + bitrev(r, ilog2(RB))];
+          if constexpr (SCALE) val = cscale(val, scale);
+          base[off + (long)(RA * r) * KS] = val;
+        });
+      }
     });
   }
 };

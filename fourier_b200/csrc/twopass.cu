@@ -16,6 +16,7 @@
 #include <cstdlib>
 
 #include "plan.h"
+#include "fused_kernels.cuh"
 #include "twopass_kernels.cuh"
 
 namespace fb200 {
@@ -30,6 +31,86 @@ namespace fb200 {
   } while (0)
 
 using namespace twopass;
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+template <typename T> struct FusedOps {
+  size_t n1, n2;
+  int ra, rb;
+  size_t smem_bytes;
+  int default_ring, default_lag;
+  cudaError_t (*prepare)();
+  cudaError_t (*launch)(const fused::FusedArgs<T>&, bool fwd, int grid, cudaStream_t);
+};
+
+template <class Cfg> struct FusedImpl {
+  using T = typename Cfg::T;
+  static cudaError_t prepare() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(fused::fused_twopass_kernel<Cfg, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES)))
+      return e;
+    return cudaFuncSetAttribute(fused::fused_twopass_kernel<Cfg, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+  }
+  static cudaError_t launch(const fused::FusedArgs<T>& a, bool fwd, int grid, cudaStream_t s) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap map;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(2 * Cfg::N2), (cuuint64_t)a.batch * (cuuint64_t)Cfg::N1};
+    const cuuint64_t gstride[1] = {(cuuint64_t)(Cfg::N2 * sizeof(cpx<T>))};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * Cfg::C), (cuuint32_t)Cfg::BOX_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    if (enc(&map, dt, 2, (void*)a.in, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_last_error("cuTensorMapEncodeTiled failed");
+      return cudaErrorInvalidValue;
+    }
+    if (fwd) fused::fused_twopass_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(map, a);
+    else fused::fused_twopass_kernel<Cfg, false><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(map, a);
+    return cudaGetLastError();
+  }
+  static const FusedOps<T>* ops(int ring, int lag) {
+    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::R, Cfg::R, Cfg::SMEM_BYTES, ring, lag,
+                                  &prepare, &launch};
+    return &o;
+  }
+};
+
+template <typename T> const FusedOps<T>* fused_lookup(size_t n);
+template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
+  if (n == ((size_t)1 << 20)) return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8>>::ops(6, 3);
+  return nullptr;
+}
+template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
+  if (n == ((size_t)1 << 16)) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4>>::ops(48, 24);
+  return nullptr;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+}  // namespace
 
 template <typename T>
 cudaError_t Plan<T>::init_twopass() {
@@ -54,6 +135,20 @@ cudaError_t Plan<T>::init_twopass() {
   if (const char* env = std::getenv("FOURIER_B200_CHUNK_MB")) mb = (size_t)std::max(1, atoi(env));
   chunk_ = std::max<size_t>(1, (mb << 20) / (n_ * sizeof(C)));
   fast_ops_ = ops;
+  // the persistent fused kernel (one launch for the whole batch) where a configuration exists
+  fused_ops_ = nullptr;
+  if (env_int("FOURIER_B200_FUSED", 1) != 0) {
+    const FusedOps<T>* f = fused_lookup<T>(n_);
+    if (f && f->n1 == n1_ && f->n2 == n2_ && f->prepare() == cudaSuccess) {
+      fused_ops_ = f;
+      ring_ = std::max(2, env_int("FOURIER_B200_RING", f->default_ring));
+      lag_ = std::min(ring_ - 1, std::max(1, env_int("FOURIER_B200_LAG", f->default_lag)));
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      sm_count_ = sms;
+    }
+  }
   return cudaSuccess;
 }
 
@@ -65,6 +160,25 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
   T scale = (T)1;
   if (code == kIfft) scale = (T)1 / (T)n_;
   else if (do_scale) scale = (T)1 / std::sqrt((T)n_);
+  if (fused_ops_ && batch <= (size_t)1 << 24) {
+    const auto* f = static_cast<const FusedOps<T>*>(fused_ops_);
+    const int ring = (int)std::min<size_t>((size_t)ring_, std::max<size_t>(batch, 2));
+    const int lag = std::min(lag_, ring - 1);
+    FB_CHECK(work_.reserve((size_t)ring * n_ * sizeof(C)));
+    const size_t cbytes = (1 + 2 * batch) * sizeof(unsigned);
+    FB_CHECK(counters_.reserve(cbytes));
+    FB_CHECK(cudaMemsetAsync(counters_.data(), 0, cbytes, s));
+    fused::FusedArgs<T> a;
+    a.in = in; a.out = out; a.scratch = (C*)work_.data();
+    a.twa1 = (const TwPair<T>*)tw_a_.data(); a.twa2 = (const TwPair<T>*)tw_b_.data();
+    a.tw2 = (const C*)tw2_.data(); a.counters = (unsigned*)counters_.data();
+    a.batch = (int)batch; a.ring = ring; a.lag = lag; a.scale = scale; a.do_scale = do_scale ? 1 : 0;
+    const size_t tiles = batch * (n1_ + n2_) / 8;
+    const int grid = (int)std::min<size_t>((size_t)sm_count_, std::max<size_t>(1, tiles / 2));
+    FB_CHECK(f->launch(a, fwd, grid, s));
+    launches_ += 1;
+    return cudaSuccess;
+  }
   const size_t chunk = std::min(chunk_, batch);
   FB_CHECK(work_.reserve(chunk * n_ * sizeof(C)));
   C* scratch = (C*)work_.data();

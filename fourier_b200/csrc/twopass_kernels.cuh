@@ -2,6 +2,7 @@
 // path.  Shared by twopass.cu (the product) and tools/emulate.cu (CPU emulation of the same code).
 #pragma once
 
+#include <cstdlib>
 #include <vector>
 
 #include "plan.h"
@@ -14,7 +15,7 @@ namespace twopass {
 // One CTA = one tile of Tile::C FFTs of one transform of the chunk.
 // The body of one tile, split at the CTA barrier so that tools/emulate.cu can run the identical code on
 // the CPU: phase1 for every thread, then phase2 for every thread.
-template <class Tile, long NS, long CS, bool LOAD_UF, long KS, long OCS, bool TW2>
+template <class Tile, class LAY, long NS, long CS, bool LOAD_UF, long KS, long OCS, bool TW2>
 struct TileBody {
   using V = typename Tile::V;
   using T = decltype(V::x);
@@ -28,14 +29,14 @@ struct TileBody {
     const V* src = a.in + b * a.batch_stride + (long)tile * a.tile_stride_in;
     f.template load<LOAD_UF, NS, CS>(t, src);
     f.template stage_a<LOAD_UF>(t, a.twa);
-    f.template scatter<LOAD_UF>(t, smem);
+    f.template scatter<LOAD_UF, LAY>(t, smem);
   }
   static FB_HD void phase2(Tile& f, const Args& a, long block, int t, const V* smem) {
     const int tile = (int)(block % a.tiles_per_fft);
     const long b = block / a.tiles_per_fft;
     V* dst = a.out + b * a.batch_stride + (long)tile * a.tile_stride_out;
     const V* t2 = TW2 ? a.tw2 + (long)tile * a.tile_stride_out : nullptr;
-    f.template gather<false>(t, smem);
+    f.template gather<false, LAY>(t, smem);
     f.stage_b();
     if (a.do_scale) f.template store<false, KS, OCS, TW2, true>(t, dst, t2, a.scale);
     else f.template store<false, KS, OCS, TW2, false>(t, dst, t2, a.scale);
@@ -43,10 +44,10 @@ struct TileBody {
 };
 
 // One CTA = one tile of Tile::C FFTs of one transform of the chunk.
-template <class Tile, long NS, long CS, bool LOAD_UF, long KS, long OCS, bool TW2, int MINB>
+template <class Tile, class LAY, long NS, long CS, bool LOAD_UF, long KS, long OCS, bool TW2, int MINB>
 __global__ void __launch_bounds__(Tile::THREADS, MINB)
-tile_kernel(const typename TileBody<Tile, NS, CS, LOAD_UF, KS, OCS, TW2>::Args a) {
-  using Body = TileBody<Tile, NS, CS, LOAD_UF, KS, OCS, TW2>;
+tile_kernel(const typename TileBody<Tile, LAY, NS, CS, LOAD_UF, KS, OCS, TW2>::Args a) {
+  using Body = TileBody<Tile, LAY, NS, CS, LOAD_UF, KS, OCS, TW2>;
   using V = typename Tile::V;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V* smem = reinterpret_cast<V*>(smem_raw);
@@ -69,16 +70,18 @@ template <typename T, int R1, int R2, int C1, int C2, int PAD1, int MINB1, int M
 struct TwoPass {
   static constexpr long N1 = (long)R1 * R1, N2 = (long)R2 * R2, N = N1 * N2;
   // pass 1: FFT length N1 over n1 (stride N2), C1 adjacent columns; both stages "col fast"
-  template <bool FWD> using Tile1 = TileFFT<T, R1, R1, R1, C1, R1 * C1 + PAD1, C1, 1, FWD>;
+  template <bool FWD> using Tile1 = TileFFT<T, R1, R1, R1, C1, FWD>;
+  using Lay1 = ExLayout<R1 * C1 + PAD1, C1, 1>;
   // pass 2: FFT length N2 over contiguous rows, C2 adjacent rows; stage A "u fast", stage B "col fast"
-  template <bool FWD> using Tile2 = TileFFT<T, R2, R2, R2, C2, R2 * C2 + 1, C2, 1, FWD>;
-  template <bool FWD> using Body1 = TileBody<Tile1<FWD>, N2, 1, false, N2, 1, true>;
-  template <bool FWD> using Body2 = TileBody<Tile2<FWD>, 1, N2, true, N1, 1, false>;
+  template <bool FWD> using Tile2 = TileFFT<T, R2, R2, R2, C2, FWD>;
+  using Lay2 = ExLayout<R2 * C2 + 1, C2, 1>;
+  template <bool FWD> using Body1 = TileBody<Tile1<FWD>, Lay1, N2, 1, false, N2, 1, true>;
+  template <bool FWD> using Body2 = TileBody<Tile2<FWD>, Lay2, 1, N2, true, N1, 1, false>;
   template <bool FWD> static constexpr auto k1() {
-    return &tile_kernel<Tile1<FWD>, N2, 1, false, N2, 1, true, MINB1>;
+    return &tile_kernel<Tile1<FWD>, Lay1, N2, 1, false, N2, 1, true, MINB1>;
   }
   template <bool FWD> static constexpr auto k2() {
-    return &tile_kernel<Tile2<FWD>, 1, N2, true, N1, 1, false, MINB2>;
+    return &tile_kernel<Tile2<FWD>, Lay2, 1, N2, true, N1, 1, false, MINB2>;
   }
   template <bool FWD>
   static typename Body1<FWD>::Args args1(const cpx<T>* in, cpx<T>* scratch, const void* twa, const cpx<T>* tw2) {
@@ -90,8 +93,8 @@ struct TwoPass {
     return {scratch, out, (const TwPair<T>*)twa, nullptr, (long)C2 * N2, C2, N, (int)(N1 / C2), scale,
             do_scale ? 1 : 0};
   }
-  static constexpr size_t smem1 = sizeof(cpx<T>) * Tile1<true>::SMEM_ELEMS;
-  static constexpr size_t smem2 = sizeof(cpx<T>) * Tile2<true>::SMEM_ELEMS;
+  static constexpr size_t smem1 = sizeof(cpx<T>) * Tile1<true>::template smem_elems<Lay1>();
+  static constexpr size_t smem2 = sizeof(cpx<T>) * Tile2<true>::template smem_elems<Lay2>();
 
   static cudaError_t prepare() {
     cudaError_t e;
@@ -125,7 +128,11 @@ struct TwoPass {
 template <typename T> const TwoPassOps<T>* lookup(size_t n);
 template <> inline const TwoPassOps<float>* lookup<float>(size_t n) {
   switch (n) {
-    case (size_t)1 << 20: return TwoPass<float, 32, 32, 8, 8, 8, 2, 2>::ops();
+    case (size_t)1 << 20: {
+      const char* env = std::getenv("FOURIER_B200_TILE");  // experiment knob: columns per tile
+      if (env && atoi(env) == 16) return TwoPass<float, 32, 32, 16, 16, 0, 1, 1>::ops();
+      return TwoPass<float, 32, 32, 8, 8, 8, 2, 2>::ops();
+    }
     case (size_t)1 << 16: return TwoPass<float, 16, 16, 16, 16, 0, 2, 2>::ops();
     case (size_t)1 << 18: return TwoPass<float, 16, 32, 16, 8, 0, 2, 2>::ops();
     default: return nullptr;

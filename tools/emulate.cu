@@ -48,10 +48,10 @@ template <int B> static int conflict_degree(const std::vector<long>& elem_index)
 }
 
 // Runs one tile body (both phases) for `blocks` CTAs on the CPU.
-template <class Body, class Tile>
+template <class Body, class Tile, class LAY>
 static void run_body(const typename Body::Args& a, long blocks) {
   using V = typename Tile::V;
-  std::vector<V> smem(Tile::SMEM_ELEMS);
+  std::vector<V> smem(Tile::template smem_elems<LAY>());
   std::vector<Tile> thr(Tile::THREADS);
   for (long b = 0; b < blocks; ++b) {
     for (int t = 0; t < Tile::THREADS; ++t) Body::phase1(thr[t], a, b, t, smem.data());
@@ -60,7 +60,7 @@ static void run_body(const typename Body::Args& a, long blocks) {
 }
 
 // Bank-conflict report for the exchange of a tile: scatter with mapping UF_A, gather with col-fast.
-template <class Tile, bool UF_A>
+template <class Tile, class LAY, bool UF_A>
 static void report_conflicts(const char* name) {
   using V = typename Tile::V;
   constexpr int B = (int)sizeof(V);
@@ -71,8 +71,8 @@ static void report_conflicts(const char* name) {
         std::vector<long> idx;
         for (int l = 0; l < 32; ++l) {
           const int t = warp * 32 + l;
-          idx.push_back((long)(Tile::template u_of<UF_A>(t) + Tile::TP * a) * Tile::SJ + (long)p * Tile::SP +
-                        (long)Tile::template col_of<UF_A>(t) * Tile::SC);
+          idx.push_back((long)(Tile::template u_of<UF_A>(t) + Tile::TP * a) * LAY::SJ + (long)p * LAY::SP +
+                        (long)Tile::template col_of<UF_A>(t) * LAY::SC);
         }
         worst_w = std::max(worst_w, conflict_degree<B>(idx));
       }
@@ -81,14 +81,14 @@ static void report_conflicts(const char* name) {
         std::vector<long> idx;
         for (int l = 0; l < 32; ++l) {
           const int t = warp * 32 + l;
-          idx.push_back((long)j * Tile::SJ + (long)(Tile::template u_of<false>(t) + Tile::TP * c) * Tile::SP +
-                        (long)Tile::template col_of<false>(t) * Tile::SC);
+          idx.push_back((long)j * LAY::SJ + (long)(Tile::template u_of<false>(t) + Tile::TP * c) * LAY::SP +
+                        (long)Tile::template col_of<false>(t) * LAY::SC);
         }
         worst_r = std::max(worst_r, conflict_degree<B>(idx));
       }
   }
   printf("  %-8s threads %4d smem %6zu B  exchange conflicts: write x%d, read x%d\n", name, Tile::THREADS,
-         sizeof(V) * Tile::SMEM_ELEMS, worst_w, worst_r);
+         sizeof(V) * Tile::template smem_elems<LAY>(), worst_w, worst_r);
 }
 
 template <typename T, class Cfg>
@@ -96,8 +96,8 @@ static int check(const char* name, double tol) {
   const long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
   const int batch = 2;
   printf("%s: N=%ld = %ld x %ld\n", name, N, N1, N2);
-  report_conflicts<typename Cfg::template Tile1<true>, false>("pass 1");
-  report_conflicts<typename Cfg::template Tile2<true>, true>("pass 2");
+  report_conflicts<typename Cfg::template Tile1<true>, typename Cfg::Lay1, false>("pass 1");
+  report_conflicts<typename Cfg::template Tile2<true>, typename Cfg::Lay2, true>("pass 2");
   int bad = 0;
   for (int fwd = 1; fwd >= 0; --fwd) {
     std::vector<cpx<T>> x((size_t)N * batch), scratch((size_t)N * batch), out((size_t)N * batch);
@@ -113,14 +113,14 @@ static int check(const char* name, double tol) {
       }
     const T scale = (T)0.5;
     if (fwd) {
-      run_body<typename Cfg::template Body1<true>, typename Cfg::template Tile1<true>>(
+      run_body<typename Cfg::template Body1<true>, typename Cfg::template Tile1<true>, typename Cfg::Lay1>(
           Cfg::template args1<true>(x.data(), scratch.data(), twa1.data(), tw2.data()), batch * (N2 / Cfg::template Tile1<true>::C));
-      run_body<typename Cfg::template Body2<true>, typename Cfg::template Tile2<true>>(
+      run_body<typename Cfg::template Body2<true>, typename Cfg::template Tile2<true>, typename Cfg::Lay2>(
           Cfg::template args2<true>(scratch.data(), out.data(), twa2.data(), scale, true), batch * (N1 / Cfg::template Tile2<true>::C));
     } else {
-      run_body<typename Cfg::template Body1<false>, typename Cfg::template Tile1<false>>(
+      run_body<typename Cfg::template Body1<false>, typename Cfg::template Tile1<false>, typename Cfg::Lay1>(
           Cfg::template args1<false>(x.data(), scratch.data(), twa1.data(), tw2.data()), batch * (N2 / Cfg::template Tile1<false>::C));
-      run_body<typename Cfg::template Body2<false>, typename Cfg::template Tile2<false>>(
+      run_body<typename Cfg::template Body2<false>, typename Cfg::template Tile2<false>, typename Cfg::Lay2>(
           Cfg::template args2<false>(scratch.data(), out.data(), twa2.data(), scale, true), batch * (N1 / Cfg::template Tile2<false>::C));
     }
     double worst = 0;
