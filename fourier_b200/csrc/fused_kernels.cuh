@@ -68,6 +68,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+// same, with an L2 evict-first hint: the transform input is read exactly once
+__device__ __forceinline__ void tma_load_2d_first(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+      "[%4], pol;\n\t}"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -120,9 +129,9 @@ template <typename T> struct FusedArgs {
   const cpx<T>* in;
   cpx<T>* out;
   cpx<T>* scratch;            // RING transforms
-  const TwPair<T>* twa1;
-  const TwPair<T>* twa2;
-  const cpx<T>* tw2;          // inter-pass twiddles, layout of the intermediate
+  const TwPair<T>* twa;       // stage-A twiddles of a length-L tile (both passes: N1 == N2 == L)
+  const cpx<T>* tbase;        // [tile][col][p]  w_N^{n2*p}        (pass-1 tile tables, contiguous per tile)
+  const cpx<T>* tstep;        // [tile][r][col]  w_N^{R*n2*r}
   unsigned* counters;         // [0] queue head, [1 .. 1+B) done1, [1+B .. 1+2B) done2
   int batch, ring, lag;
   T scale;
@@ -138,60 +147,70 @@ struct FusedCfg {
   template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
   using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
   using Lay2 = ExLayout<R * C + 1, C, 1>;                          // pass 2: scatter u-fast, gather col-fast
-  static constexpr int GT = R * C;                    // threads per consumer group
-  static constexpr int CONSUMERS = G * GT;
-  static constexpr int THREADS = CONSUMERS;           // thread 0 of each group doubles as its TMA producer
+  static constexpr int GT = R * C;                    // threads per group
+  static constexpr int THREADS = G * GT;              // thread 0 of each group doubles as its TMA producer
   static constexpr int T1 = (int)(N2 / C), T2 = (int)(N1 / C);
   static constexpr uint32_t TILE_BYTES = (uint32_t)(sizeof(cpx<T>) * C * L);
+  static constexpr uint32_t TAB_BYTES = (uint32_t)(sizeof(cpx<T>) * C * R);   // one tile table (base or step)
   static constexpr int EX1 = Tile<true>::template smem_elems<Lay1>(), EX2 = Tile<true>::template smem_elems<Lay2>();
   static constexpr int EX_ELEMS = EX1 > EX2 ? EX1 : EX2;
   static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * EX_ELEMS + 127) / 128) * 128;
-  static constexpr size_t SMEM_BYTES = (size_t)G * TILE_BYTES + EX_BYTES + 256 + 1024 /*alignment slack*/;
+  static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (R / 2) * R;
+  // layout: staging[G] | exchange | twa | tile tables [G][2 bufs][base, step] | control
+  static constexpr size_t OFF_EX = (size_t)G * TILE_BYTES;
+  static constexpr size_t OFF_TWA = OFF_EX + EX_BYTES;
+  static constexpr size_t OFF_TAB = OFF_TWA + TWA_BYTES;
+  static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 4 * TAB_BYTES;
+  static constexpr size_t SMEM_BYTES = OFF_CTL + 128 + 128 /*alignment slack*/;
   static constexpr int BOX_ROWS = L < 256 ? (int)L : 256;   // TMA box limit: 256 per dimension
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
-// Issues the loads of one work item into staging buffer `dst` (called by one thread of the group).
+struct GroupCtl {            // per-group control block in shared memory
+  uint64_t full;             // TMA for the group's next tile has landed
+  uint64_t empty;            // every thread of the group has pulled its samples out of staging
+  WorkItem desc;             // the tile the staging buffer holds / will hold
+  int pad;
+};
+
+// Issues the loads of one work item into the group's staging buffer (one thread of the group).
 template <class Cfg>
 __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap* in_map,
                                            const FusedArgs<typename Cfg::T>& a, cpx<typename Cfg::T>* dst,
-                                           uint64_t* full, WorkItem* desc) {
+                                           cpx<typename Cfg::T>* tab, GroupCtl* ctl) {
   using V = cpx<typename Cfg::T>;
   constexpr int C = Cfg::C;
-  *desc = wi;
-  if (wi.pass < 0) { mbar_arrive(full); return; }
+  ctl->desc = wi;
+  if (wi.pass < 0) { mbar_arrive(&ctl->full); return; }
   fence_proxy_async();   // the group's generic-proxy reads of `dst` precede the async-proxy refill
-  mbar_arrive_expect_tx(full, Cfg::TILE_BYTES);
   if (wi.pass == 1) {
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + 2 * Cfg::TAB_BYTES);
     constexpr int BOX = Cfg::BOX_ROWS;
     const int x = wi.tile * C * 2;  // in scalars of T
 #pragma unroll
     for (int r0 = 0; r0 < (int)Cfg::L; r0 += BOX)
-      tma_load_2d(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), full);
+      tma_load_2d_first(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), &ctl->full);
+    bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
   } else {
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES);
     const V* src = a.scratch + (size_t)(wi.b % a.ring) * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
     constexpr uint32_t PIECE = 16384;
 #pragma unroll
     for (uint32_t o = 0; o < Cfg::TILE_BYTES; o += PIECE)
       bulk_load((unsigned char*)dst + o, (const unsigned char*)src + o,
-                Cfg::TILE_BYTES - o < PIECE ? Cfg::TILE_BYTES - o : PIECE, full);
+                Cfg::TILE_BYTES - o < PIECE ? Cfg::TILE_BYTES - o : PIECE, &ctl->full);
   }
 }
 
-// Dependencies of a work item: returns true when they are satisfied (non-blocking probe).
+// Address of the counter a work item depends on (nullptr: no dependency) and the value it must reach.
 template <class Cfg>
-__device__ __forceinline__ bool deps_ready(const WorkItem& wi, const FusedArgs<typename Cfg::T>& a) {
-  const unsigned* done1 = a.counters + 1;
-  const unsigned* done2 = a.counters + 1 + a.batch;
-  if (wi.pass == 1 && wi.b >= a.ring) return ld_acquire(&done2[wi.b - a.ring]) >= (unsigned)Cfg::T2;
-  if (wi.pass == 2) return ld_acquire(&done1[wi.b]) >= (unsigned)Cfg::T1;
-  return true;
-}
-template <class Cfg>
-__device__ __forceinline__ void deps_wait(const WorkItem& wi, const FusedArgs<typename Cfg::T>& a) {
-  for (unsigned spins = 0; !deps_ready<Cfg>(wi, a); ++spins) {
-    if (spins > (1u << 24)) __trap();
-    __nanosleep(100);
-  }
+__device__ __forceinline__ const unsigned* dep_counter(const WorkItem& wi, const FusedArgs<typename Cfg::T>& a,
+                                                       unsigned* target) {
+  if (wi.pass == 1 && wi.b >= a.ring) { *target = (unsigned)Cfg::T2; return a.counters + 1 + a.batch + (wi.b - a.ring); }
+  if (wi.pass == 2) { *target = (unsigned)Cfg::T1; return a.counters + 1 + wi.b; }
+  *target = 0;
+  return nullptr;
 }
 
 template <class Cfg, bool FWD>
@@ -199,26 +218,29 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs<typename Cfg::T> a) {
   using T = typename Cfg::T;
   using V = cpx<T>;
-  constexpr int G = Cfg::G, GT = Cfg::GT, C = Cfg::C;
+  constexpr int G = Cfg::G, GT = Cfg::GT, C = Cfg::C, R = Cfg::R;
   constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2, L = Cfg::L;
   constexpr int T1 = Cfg::T1, T2 = Cfg::T2;
+  using Tile = typename Cfg::template Tile<FWD>;
+  using Lay1 = typename Cfg::Lay1;
+  using Lay2 = typename Cfg::Lay2;
 
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  V* staging = reinterpret_cast<V*>(base);                                        // [G][C*L]
-  V* exch = reinterpret_cast<V*>(base + (size_t)G * Cfg::TILE_BYTES);
-  unsigned char* ctl = base + (size_t)G * Cfg::TILE_BYTES + Cfg::EX_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ctl);            // [G] TMA landed
-  uint64_t* empty = full + G;                                   // [G] staging consumed by the whole group
-  WorkItem* desc = reinterpret_cast<WorkItem*>(empty + G);      // [G]
-  int* lock = reinterpret_cast<int*>(desc + G);
+  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  V* staging = reinterpret_cast<V*>(base);                                   // [G][C*L]
+  V* exch = reinterpret_cast<V*>(base + Cfg::OFF_EX);
+  TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
+  V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][2][2][C*R]
+  GroupCtl* ctl_all = reinterpret_cast<GroupCtl*>(base + Cfg::OFF_CTL);
+  int* lock = reinterpret_cast<int*>(ctl_all + G);
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int g = 0; g < G; ++g) { mbar_init(&full[g], 1); mbar_init(&empty[g], GT); }
+    for (int g = 0; g < G; ++g) { mbar_init(&ctl_all[g].full, 1); mbar_init(&ctl_all[g].empty, GT); }
     *lock = 0;
     fence_barrier_init();
   }
+  for (int i = tid; i < (R / 2) * R; i += Cfg::THREADS) twa[i] = a.twa[i];   // stage-A twiddles live in smem
   __syncthreads();
 
   unsigned* queue = a.counters;
@@ -228,79 +250,102 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   const int g = tid / GT;
   const int t = tid - g * GT;
   V* stage_g = staging + (size_t)g * C * L;
+  V* tab_g = tabs + (size_t)g * 4 * C * R;
+  GroupCtl* ctl = &ctl_all[g];
   const int bar_id = 1 + g;
-  using Tile = typename Cfg::template Tile<FWD>;
-  using Lay1 = typename Cfg::Lay1;
-  using Lay2 = typename Cfg::Lay2;
 
-  // Thread 0 of each group is the group's producer: it claims queue items one ahead (`nxt`), and
-  // issues the TMA for the next tile as soon as the current one has left the staging buffer.
-  WorkItem nxt = {-1, 0, 0};
+  // Thread 0 of each group is the group's producer.  It keeps one claimed-but-not-issued queue
+  // position (`nxt_raw`; the atomicAdd that produced it was issued a whole tile earlier, so its latency
+  // is never on the critical path) and refills the staging buffer as soon as the group has emptied it.
+  unsigned nxt_raw = 0;
   bool exhausted = false;
+  uint32_t n_p1 = 0;   // pass-1 tiles issued so far by this group: selects the tile-table buffer
   if (t == 0) {
-    WorkItem first = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
-    deps_wait<Cfg>(first, a);
-    issue_tile<Cfg>(first, &in_map, a, stage_g, &full[g], &desc[g]);
+    const WorkItem first = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+    unsigned target;
+    const unsigned* dep = dep_counter<Cfg>(first, a, &target);
+    if (dep) { spin_until_ge(dep, target); fence_proxy_async(); }
+    issue_tile<Cfg>(first, &in_map, a, stage_g, tab_g, ctl);
+    n_p1 += first.pass == 1;
     exhausted = first.pass < 0;
-    if (!exhausted) nxt = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+    if (!exhausted) nxt_raw = atomicAdd(queue, 1u);
   }
+  uint32_t k_p1 = 0;   // pass-1 tiles consumed so far by this group (all threads track it)
 
   for (uint32_t k = 0;; ++k) {
-    mbar_wait(&full[g], k & 1);
-    const WorkItem wi = desc[g];
+    mbar_wait(&ctl->full, k & 1);
+    const WorkItem wi = ctl->desc;
     if (wi.pass < 0) break;
-    bool pending = false;
 
-    // ---- phase 1: staging -> registers, stage A, then hand the staging buffer back ----------------------
-    Tile f;
-    if (wi.pass == 1) {
-      f.template load<false, C, 1>(t, stage_g);        // staging = [n1][C]
-      f.template stage_a<false>(t, a.twa1);
-    } else {
-      f.template load<true, 1, N2>(t, stage_g);        // staging = C contiguous rows
-      f.template stage_a<true>(t, a.twa2);
+    // producer, step 1: decode the next item and start probing its dependency (latency hidden by the loads)
+    WorkItem nxt = {-1, 0, 0};
+    unsigned dep_target = 0, dep_seen = 0;
+    const unsigned* dep = nullptr;
+    if (t == 0 && !exhausted) {
+      nxt = decode_work((long)nxt_raw, a.batch, a.lag, T1, T2);
+      dep = dep_counter<Cfg>(nxt, a, &dep_target);
+      if (dep) dep_seen = ld_acquire(dep);
     }
-    mbar_arrive(&empty[g]);
+
+    // ---- staging -> registers; the staging buffer is free again as soon as every thread has its samples ----
+    Tile f;
+    if (wi.pass == 1) f.template load<false, C, 1>(t, stage_g);        // staging = [n1][C]
+    else f.template load<true, 1, N2>(t, stage_g);                     // staging = C contiguous rows
+    mbar_arrive(&ctl->empty);
+
+    bool pending = false;
     if (t == 0) {
-      mbar_wait(&empty[g], k & 1);                     // every thread of the group has its samples
-      if (wi.pass == 2) red_release_add(&done2[wi.b], 1u);   // ring slot consumed by this tile
+      mbar_wait(&ctl->empty, k & 1);
+      if (wi.pass == 2) atomicAdd(&done2[wi.b], 1u);                   // ring slot consumed by this tile
       if (!exhausted) {
-        if (deps_ready<Cfg>(nxt, a)) {
-          issue_tile<Cfg>(nxt, &in_map, a, stage_g, &full[g], &desc[g]);
+        if (!dep || dep_seen >= dep_target) {
+          if (dep) fence_proxy_async();
+          issue_tile<Cfg>(nxt, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
+          n_p1 += nxt.pass == 1;
           exhausted = nxt.pass < 0;
-          if (!exhausted) nxt = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+          if (!exhausted) nxt_raw = atomicAdd(queue, 1u);
         } else {
-          pending = true;                              // never block here: our own tile may be the dependency
+          pending = true;      // never block here: this group's own tile may be (part of) the dependency
         }
       }
+    }
+
+    if (wi.pass == 1) f.template stage_a<false>(t, twa); else f.template stage_a<true>(t, twa);
+
+    // ---- exchange through the shared buffer, under the CTA-wide lock -----------------------------------------
+    if (t == 0) {
       unsigned spins = 0;
       while (atomicCAS(lock, 0, 1) != 0) if (++spins > (1u << 26)) __trap();
     }
-    // ---- phase 2: exchange through the shared buffer (held under the lock) ---------------------------------
     group_sync(bar_id, GT);
     if (wi.pass == 1) f.template scatter<false, Lay1>(t, exch); else f.template scatter<true, Lay2>(t, exch);
     group_sync(bar_id, GT);
     if (wi.pass == 1) f.template gather<false, Lay1>(t, exch); else f.template gather<false, Lay2>(t, exch);
     group_sync(bar_id, GT);
     if (t == 0) { __threadfence_block(); atomicExch(lock, 0); }
-    // ---- phase 3: stage B and the stores --------------------------------------------------------------------
+
+    // ---- stage B and the stores ---------------------------------------------------------------------------------
+    f.stage_b();
     if (wi.pass == 1) {
-      f.stage_b();
+      const V* tb = tab_g + (size_t)(k_p1 & 1) * 2 * C * R;
+      ++k_p1;
       V* dst = a.scratch + (size_t)(wi.b % a.ring) * N + (size_t)wi.tile * C;
-      f.template store<false, N2, 1, true, false>(t, dst, a.tw2 + (size_t)wi.tile * C, (T)1);
+      f.template store_factored<N2, 1, 2>(t, dst, tb, tb + C * R);       // intermediate: keep in L2
       group_sync(bar_id, GT);
       if (t == 0) { __threadfence(); red_release_add(&done1[wi.b], 1u); }
     } else {
-      f.stage_b();
       V* dst = a.out + (size_t)wi.b * N + (size_t)wi.tile * C;
-      if (a.do_scale) f.template store<false, N1, 1, false, true>(t, dst, nullptr, a.scale);
-      else f.template store<false, N1, 1, false, false>(t, dst, nullptr, a.scale);
+      if (a.do_scale) f.template store<false, N1, 1, false, true, 1>(t, dst, nullptr, a.scale);   // streaming
+      else f.template store<false, N1, 1, false, false, 1>(t, dst, nullptr, a.scale);
     }
+
     if (t == 0 && pending) {
-      deps_wait<Cfg>(nxt, a);
-      issue_tile<Cfg>(nxt, &in_map, a, stage_g, &full[g], &desc[g]);
+      spin_until_ge(dep, dep_target);
+      fence_proxy_async();
+      issue_tile<Cfg>(nxt, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
+      n_p1 += nxt.pass == 1;
       exhausted = nxt.pass < 0;
-      if (!exhausted) nxt = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
+      if (!exhausted) nxt_raw = atomicAdd(queue, 1u);
     }
   }
 }

@@ -26,6 +26,34 @@
 
 namespace fb200 {
 
+// Global store with an L2 eviction hint: 0 = default, 1 = streaming / evict-first (data that is not
+// read again: the transform output), 2 = evict-last (data that should stay in L2: the intermediate).
+template <int HINT, typename V> FB_HD void st_hint(V* p, const V& v) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (HINT == 0) {
+    *p = v;
+  } else if constexpr (sizeof(V) == 8) {
+    if constexpr (HINT == 1) {
+      asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+          "st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, pol;\n\t}" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+    }
+  } else {
+    if constexpr (HINT == 1) {
+      asm volatile("st.global.cs.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+          "st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, pol;\n\t}" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+    }
+  }
+#else
+  *p = v;
+#endif
+}
+
 // Two consecutive twiddles, loaded with one 128-bit (f32) / two 128-bit (f64) instructions.
 template <typename T> struct alignas(2 * sizeof(cpx<T>)) TwPair { cpx<T> a, b; };
 
@@ -122,7 +150,7 @@ struct TileFFT {
   // registers -> global.  Output k = p + RA*r of FFT `col` goes to base[col*CS + k*KS], optionally
   // multiplied by the inter-pass twiddle tw2[col*CS + k*KS] (same layout as the destination) and by
   // a real scale factor.
-  template <bool UF, long KS, long CS, bool TW2, bool SCALE>
+  template <bool UF, long KS, long CS, bool TW2, bool SCALE, int HINT = 0>
   FB_HD void store(int t, V* __restrict__ base, const V* __restrict__ tw2, T scale) const {
     const int col = col_of<UF>(t), u = u_of<UF>(t);
     static_for<0, NB>([&](auto Cc) {
@@ -146,7 +174,7 @@ struct TileFFT {
             constexpr int r = g * TWB + decltype(Q)::value;
             V val = ctw<FWD>(v[c * RB + bitrev(r, ilog2(RB))], w[decltype(Q)::value]);
             if constexpr (SCALE) val = cscale(val, scale);
-            base[off + (long)(RA * r) * KS] = val;
+            st_hint<HINT>(&base[off + (long)(RA * r) * KS], val);
           });
           if constexpr ((g + 1) * TWB < RB) {
 #pragma unroll
@@ -158,9 +186,29 @@ struct TileFFT {
           constexpr int r = decltype(Rr)::value;
           V val = v[c * RB + bitrev(r, ilog2(RB))];
           if constexpr (SCALE) val = cscale(val, scale);
-          base[off + (long)(RA * r) * KS] = val;
+          st_hint<HINT>(&base[off + (long)(RA * r) * KS], val);
         });
       }
+    });
+  }
+
+  // Pass-1 store with the inter-pass twiddle in factored form, both factors in shared memory:
+  //   w_N^{n2*(p + RA*r)} = base[n2][p] * step[n2][r],  base = w_N^{n2*p},  step = w_N^{RA*n2*r}.
+  // sbase is laid out [col][p], sstep [r][col] (lanes that differ in col read adjacent words, lanes that
+  // differ in p broadcast).  Costs one extra complex multiply per sample and no global-memory load.
+  template <long KS, long CS, int HINT>
+  FB_HD void store_factored(int t, V* __restrict__ base, const V* sbase, const V* sstep) const {
+    const int col = col_of<false>(t), u = u_of<false>(t);
+    static_for<0, NB>([&](auto Cc) {
+      constexpr int c = decltype(Cc)::value;
+      const int p = u + TP * c;
+      const long off = (long)col * CS + (long)p * KS;
+      const V wb = sbase[col * RA + p];
+      static_for<0, RB>([&](auto Rr) {
+        constexpr int r = decltype(Rr)::value;
+        const V w = cmul(wb, sstep[r * C + col]);
+        st_hint<HINT>(&base[off + (long)(RA * r) * KS], ctw<FWD>(v[c * RB + bitrev(r, ilog2(RB))], w));
+      });
     });
   }
 };

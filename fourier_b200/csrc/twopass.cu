@@ -52,7 +52,7 @@ EncodeTiledFn encode_tiled() {
 
 template <typename T> struct FusedOps {
   size_t n1, n2;
-  int ra, rb;
+  int ra, rb, tile_c;
   size_t smem_bytes;
   int default_ring, default_lag;
   cudaError_t (*prepare)();
@@ -89,7 +89,7 @@ template <class Cfg> struct FusedImpl {
     return cudaGetLastError();
   }
   static const FusedOps<T>* ops(int ring, int lag) {
-    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::R, Cfg::R, Cfg::SMEM_BYTES, ring, lag,
+    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::R, Cfg::R, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
                                   &prepare, &launch};
     return &o;
   }
@@ -140,6 +140,22 @@ cudaError_t Plan<T>::init_twopass() {
   if (env_int("FOURIER_B200_FUSED", 1) != 0) {
     const FusedOps<T>* f = fused_lookup<T>(n_);
     if (f && f->n1 == n1_ && f->n2 == n2_ && f->prepare() == cudaSuccess) {
+      // factored inter-pass twiddles, contiguous per pass-1 tile of `tile_c` columns:
+      //   tbase[tile][col][p] = w_N^{n2*p},  tstep[tile][r][col] = w_N^{R*n2*r},  n2 = tile*tile_c + col
+      const int rr = f->ra, cc = f->tile_c;
+      std::vector<cpx<T>> tb((size_t)n2_ * rr), ts((size_t)n2_ * rr);
+      for (size_t c2 = 0; c2 < n2_; ++c2) {
+        const size_t tile = c2 / cc, col = c2 % cc;
+        for (int q = 0; q < rr; ++q) {
+          double re, im;
+          host_twiddle(c2 * (size_t)q, n_, &re, &im);
+          tb[(tile * cc + col) * rr + q] = mk<T>((T)re, (T)im);
+          host_twiddle((size_t)rr * c2 * (size_t)q, n_, &re, &im);
+          ts[(tile * rr + q) * cc + col] = mk<T>((T)re, (T)im);
+        }
+      }
+      FB_CHECK((upload_vec<T, cpx<T>>(tbase_, tb)));
+      FB_CHECK((upload_vec<T, cpx<T>>(tstep_, ts)));
       fused_ops_ = f;
       ring_ = std::max(2, env_int("FOURIER_B200_RING", f->default_ring));
       lag_ = std::min(ring_ - 1, std::max(1, env_int("FOURIER_B200_LAG", f->default_lag)));
@@ -170,8 +186,9 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
     FB_CHECK(cudaMemsetAsync(counters_.data(), 0, cbytes, s));
     fused::FusedArgs<T> a;
     a.in = in; a.out = out; a.scratch = (C*)work_.data();
-    a.twa1 = (const TwPair<T>*)tw_a_.data(); a.twa2 = (const TwPair<T>*)tw_b_.data();
-    a.tw2 = (const C*)tw2_.data(); a.counters = (unsigned*)counters_.data();
+    a.twa = (const TwPair<T>*)tw_a_.data();
+    a.tbase = (const C*)tbase_.data(); a.tstep = (const C*)tstep_.data();
+    a.counters = (unsigned*)counters_.data();
     a.batch = (int)batch; a.ring = ring; a.lag = lag; a.scale = scale; a.do_scale = do_scale ? 1 : 0;
     const size_t tiles = batch * (n1_ + n2_) / 8;
     const int grid = (int)std::min<size_t>((size_t)sm_count_, std::max<size_t>(1, tiles / 2));
