@@ -1,11 +1,12 @@
 // fused_kernels.cuh -- the flagship kernel: both passes of the four-step FFT in ONE persistent,
 // warp-specialised launch.
 //
-//   * one CTA per SM, G groups of threads, each processing one TileFFT tile in registers at a time;
-//   * thread 0 of a group is its producer: it claims items of a global work queue (atomic counter)
-//     whose order interleaves pass-1 tiles of transform s with pass-2 tiles of transform s-LAG,
-//     probes the tile's dependencies, and brings the tile into the group's shared-memory staging
-//     buffer with TMA: a 2-D tensor-map box for the
+//   * one CTA per SM: G consumer groups, each processing one TileFFT tile in registers at a time, and
+//     one producer warp (a first version let thread 0 of each group produce: the ~3000 cycles of
+//     queue/TMA work per tile then sat on the critical path of its group's first barrier);
+//   * the producer claims items of a global work queue (atomic counter) whose order interleaves
+//     pass-1 tiles of transform s with pass-2 tiles of transform s-LAG, waits for the tile's
+//     dependencies, and brings the tile into the target group's shared-memory staging buffer with TMA: a 2-D tensor-map box for the
 //     strided column tiles of pass 1 (cp.async.bulk.tensor), plain bulk copies for the contiguous
 //     row tiles of pass 2 (cp.async.bulk) -- completion is signalled on an mbarrier (full[g]);
 //   * a consumer group waits on full[g], pulls its 32 (16) samples per thread out of the staging
@@ -90,6 +91,19 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned atom_add_acq_rel_cta_shared(unsigned* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void st_release_cta_shared(unsigned* p, unsigned v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_cta_shared(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 __device__ __forceinline__ void spin_until_ge(const unsigned* p, unsigned target) {
   for (unsigned spins = 0; ld_acquire(p) < target; ++spins) {
     if (spins > (1u << 24)) __trap();
@@ -101,11 +115,11 @@ __device__ __forceinline__ void group_sync(int id, int threads) {
 }
 
 // ---- work queue ---------------------------------------------------------------------------------------------
-struct WorkItem { int pass, b, tile; };  // pass: 1, 2, or -1 = queue exhausted
+struct WorkItem { int pass, b, tile, slot; };  // pass: 1, 2, or -1 = queue exhausted; slot = b % ring
 
 // Queue order: slot s = 0 .. B+LAG-1 holds [pass-1 tiles of transform s] then [pass-2 tiles of s-LAG].
 __host__ __device__ inline WorkItem decode_work(long w, int batch, int lag, int t1, int t2) {
-  WorkItem it = {-1, 0, 0};
+  WorkItem it = {-1, 0, 0, 0};
   const long total = (long)batch * (t1 + t2);
   if (w >= total) return it;
   const int d = lag < batch ? lag : batch;
@@ -136,6 +150,7 @@ template <typename T> struct FusedArgs {
   int batch, ring, lag;
   T scale;
   int do_scale;
+  long long* trace;           // optional phase timestamps of CTA 0 (debugging / DESIGN.md timeline), else nullptr
 };
 
 // Configuration: N = (R*R)^2, tiles of C FFTs, G consumer groups per CTA.
@@ -148,7 +163,15 @@ struct FusedCfg {
   using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
   using Lay2 = ExLayout<R * C + 1, C, 1>;                          // pass 2: scatter u-fast, gather col-fast
   static constexpr int GT = R * C;                    // threads per group
-  static constexpr int THREADS = G * GT;              // thread 0 of each group doubles as its TMA producer
+  static constexpr int CONSUMERS = G * GT;
+  static constexpr int THREADS = CONSUMERS + 128;     // + one producer warpgroup (one lane of it works)
+  // Register budget.  Registers are handed out per 4 warps, so a 17th warp costs as much as 4; the
+  // producer warpgroup therefore gives its registers back (setmaxnreg.dec) and the consumers take
+  // them (setmaxnreg.inc): LAUNCH_REGS per thread at launch, REGS_CONSUMER / REGS_PRODUCER afterwards.
+  static constexpr int LAUNCH_REGS = ((65536 / THREADS) / 8) * 8;
+  static constexpr int REGS_PRODUCER = 24;
+  static constexpr int REGS_CONSUMER_RAW = ((LAUNCH_REGS * THREADS - REGS_PRODUCER * 128) / CONSUMERS / 8) * 8;
+  static constexpr int REGS_CONSUMER = REGS_CONSUMER_RAW > 232 ? 232 : REGS_CONSUMER_RAW;
   static constexpr int T1 = (int)(N2 / C), T2 = (int)(N1 / C);
   static constexpr uint32_t TILE_BYTES = (uint32_t)(sizeof(cpx<T>) * C * L);
   static constexpr uint32_t TAB_BYTES = (uint32_t)(sizeof(cpx<T>) * C * R);   // one tile table (base or step)
@@ -161,16 +184,23 @@ struct FusedCfg {
   static constexpr size_t OFF_TWA = OFF_EX + EX_BYTES;
   static constexpr size_t OFF_TAB = OFF_TWA + TWA_BYTES;
   static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 4 * TAB_BYTES;
-  static constexpr size_t SMEM_BYTES = OFF_CTL + 128 + 128 /*alignment slack*/;
+  static constexpr size_t SMEM_BYTES = OFF_CTL + 512 /* control block: G * sizeof(GroupCtl) + lock */;
   static constexpr int BOX_ROWS = L < 256 ? (int)L : 256;   // TMA box limit: 256 per dimension
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
+
+constexpr int kStoreRing = 16;
 
 struct GroupCtl {            // per-group control block in shared memory
   uint64_t full;             // TMA for the group's next tile has landed
   uint64_t empty;            // every thread of the group has pulled its samples out of staging
   WorkItem desc;             // the tile the staging buffer holds / will hold
-  int pad;
+  int loaded;                // warps of the group that have pulled their samples out of staging (this tile)
+  unsigned stored_warps;     // warps of the group that have issued the stores of the current pass-1 tile
+  unsigned stored_seq;       // pass-1 tiles of this group whose stores have all been issued
+  unsigned finished;         // the group has left its tile loop
+  unsigned acked;            // pass-1 tiles of this group the signaller has published (back-pressure)
+  int store_b[kStoreRing];   // transform index of pass-1 tile number n at [n % kStoreRing]
 };
 
 // Issues the loads of one work item into the group's staging buffer (one thread of the group).
@@ -180,9 +210,11 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
                                            cpx<typename Cfg::T>* tab, GroupCtl* ctl) {
   using V = cpx<typename Cfg::T>;
   constexpr int C = Cfg::C;
-  ctl->desc = wi;
+  WorkItem d = wi;
+  d.slot = wi.b & (a.ring - 1);               // ring is a power of two
+  ctl->desc = d;
   if (wi.pass < 0) { mbar_arrive(&ctl->full); return; }
-  fence_proxy_async();   // the group's generic-proxy reads of `dst` precede the async-proxy refill
+  // (the group's reads of `dst` are ordered before this refill by the empty-mbarrier wait of the caller)
   if (wi.pass == 1) {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + 2 * Cfg::TAB_BYTES);
     constexpr int BOX = Cfg::BOX_ROWS;
@@ -194,7 +226,7 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
     bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
   } else {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES);
-    const V* src = a.scratch + (size_t)(wi.b % a.ring) * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
+    const V* src = a.scratch + (size_t)d.slot * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
     constexpr uint32_t PIECE = 16384;
 #pragma unroll
     for (uint32_t o = 0; o < Cfg::TILE_BYTES; o += PIECE)
@@ -213,6 +245,19 @@ __device__ __forceinline__ const unsigned* dep_counter(const WorkItem& wi, const
   return nullptr;
 }
 
+constexpr int kTraceTiles = 64, kTracePhases = 8;
+#define FB_TRACE(phase)                                                                                   \
+  do {                                                                                                    \
+    if (a.trace && blockIdx.x == 0 && (t & 31) == 0 && k < kTraceTiles)                                   \
+      a.trace[(((long)g * (GT / 32) + (t >> 5)) * kTraceTiles + k) * kTracePhases + (phase)] = clock64(); \
+  } while (0)
+
+#define FB_PTRACE(phase)                                                                                  \
+  do {                                                                                                    \
+    if (a.trace && blockIdx.x == 0 && it < kTraceTiles)                                                   \
+      a.trace[(((long)(Cfg::CONSUMERS / 32) + g) * kTraceTiles + it) * kTracePhases + (phase)] = clock64(); \
+  } while (0)
+
 template <class Cfg, bool FWD>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs<typename Cfg::T> a) {
@@ -225,8 +270,10 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   using Lay1 = typename Cfg::Lay1;
   using Lay2 = typename Cfg::Lay2;
 
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+  // No integer round-trip on this pointer: the compiler must keep the shared address space, otherwise
+  // every staging/exchange access becomes a generic LD/ST (seen in the first profile of this kernel).
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* base = smem_raw;
   V* staging = reinterpret_cast<V*>(base);                                   // [G][C*L]
   V* exch = reinterpret_cast<V*>(base + Cfg::OFF_EX);
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
@@ -236,7 +283,15 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int g = 0; g < G; ++g) { mbar_init(&ctl_all[g].full, 1); mbar_init(&ctl_all[g].empty, GT); }
+    for (int g = 0; g < G; ++g) {
+      mbar_init(&ctl_all[g].full, 1);
+      mbar_init(&ctl_all[g].empty, GT);
+      ctl_all[g].loaded = 0;
+      ctl_all[g].stored_warps = 0;
+      ctl_all[g].stored_seq = 0;
+      ctl_all[g].finished = 0;
+      ctl_all[g].acked = 0;
+    }
     *lock = 0;
     fence_barrier_init();
   }
@@ -247,68 +302,100 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   unsigned* done1 = a.counters + 1;
   unsigned* done2 = a.counters + 1 + a.batch;
 
+  if (tid >= Cfg::CONSUMERS) {
+    // =============================== producer warpgroup =======================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_PRODUCER));
+    const int pw = (tid - Cfg::CONSUMERS) >> 5;
+    if ((tid & 31) != 0) return;
+    if (pw < G) {
+      // ---- producer of group pw: claim a queue item (one ahead, so the atomic's latency is hidden), wait for
+      // its dependencies (blocking is fine here: nothing a consumer needs is held back by it), wait until
+      // the group has emptied its staging buffer, refill it by TMA.
+      const int g = pw;
+      GroupCtl* ctl = &ctl_all[g];
+      V* stage_g = staging + (size_t)g * C * L;
+      V* tab_g = tabs + (size_t)g * 4 * C * R;
+      uint32_t n_p1 = 0;
+      unsigned w_next = atomicAdd(queue, 1u);
+      for (uint32_t it = 0;; ++it) {
+        const WorkItem wi = decode_work((long)w_next, a.batch, a.lag, T1, T2);
+        if (wi.pass >= 0) w_next = atomicAdd(queue, 1u);
+        FB_PTRACE(0);
+        unsigned target;
+        const unsigned* dep = dep_counter<Cfg>(wi, a, &target);
+        if (dep) { spin_until_ge(dep, target); fence_proxy_async(); }
+        FB_PTRACE(1);
+        if (it > 0) mbar_wait(&ctl->empty, (it - 1) & 1);
+        FB_PTRACE(2);
+        issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
+        FB_PTRACE(3);
+        n_p1 += wi.pass == 1;
+        if (wi.pass < 0) break;
+      }
+    } else if (pw == G) {
+      // ---- signaller: publishes finished pass-1 tiles.  The gpu-scope release fence costs ~2500 cycles; on a
+      // consumer thread it delayed that thread's warp, and with it the whole group at its next barrier.
+      unsigned seen[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) seen[g] = 0;
+      for (unsigned idle = 0;;) {
+        unsigned seq[G];
+        bool all_done = true, work = false;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const unsigned fin = ld_acquire_cta_shared(&ctl_all[g].finished);   // read before seq: no tile is missed
+          seq[g] = ld_acquire_cta_shared(&ctl_all[g].stored_seq);
+          work = work || seen[g] < seq[g];
+          all_done = all_done && fin && seen[g] == seq[g];
+        }
+        if (work) {
+          __threadfence();   // every store the groups issued for tiles < seq[g] is visible gpu-wide after this
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            for (; seen[g] < seq[g]; ++seen[g]) atomicAdd(&done1[ctl_all[g].store_b[seen[g] % kStoreRing]], 1u);
+            st_release_cta_shared(&ctl_all[g].acked, seen[g]);
+          }
+          idle = 0;
+        } else {
+          if (all_done) break;
+          __nanosleep(100);
+          if (++idle > (1u << 26)) __trap();
+        }
+      }
+    }
+    return;
+  }
+
+  // ======================================= consumer groups =====================================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_CONSUMER));
   const int g = tid / GT;
   const int t = tid - g * GT;
   V* stage_g = staging + (size_t)g * C * L;
   V* tab_g = tabs + (size_t)g * 4 * C * R;
   GroupCtl* ctl = &ctl_all[g];
   const int bar_id = 1 + g;
-
-  // Thread 0 of each group is the group's producer.  It keeps one claimed-but-not-issued queue
-  // position (`nxt_raw`; the atomicAdd that produced it was issued a whole tile earlier, so its latency
-  // is never on the critical path) and refills the staging buffer as soon as the group has emptied it.
-  unsigned nxt_raw = 0;
-  bool exhausted = false;
-  uint32_t n_p1 = 0;   // pass-1 tiles issued so far by this group: selects the tile-table buffer
-  if (t == 0) {
-    const WorkItem first = decode_work((long)atomicAdd(queue, 1u), a.batch, a.lag, T1, T2);
-    unsigned target;
-    const unsigned* dep = dep_counter<Cfg>(first, a, &target);
-    if (dep) { spin_until_ge(dep, target); fence_proxy_async(); }
-    issue_tile<Cfg>(first, &in_map, a, stage_g, tab_g, ctl);
-    n_p1 += first.pass == 1;
-    exhausted = first.pass < 0;
-    if (!exhausted) nxt_raw = atomicAdd(queue, 1u);
-  }
-  uint32_t k_p1 = 0;   // pass-1 tiles consumed so far by this group (all threads track it)
+  uint32_t k_p1 = 0;   // pass-1 tiles consumed so far by this group: selects the tile-table buffer
 
   for (uint32_t k = 0;; ++k) {
+    FB_TRACE(0);
     mbar_wait(&ctl->full, k & 1);
     const WorkItem wi = ctl->desc;
     if (wi.pass < 0) break;
-
-    // producer, step 1: decode the next item and start probing its dependency (latency hidden by the loads)
-    WorkItem nxt = {-1, 0, 0};
-    unsigned dep_target = 0, dep_seen = 0;
-    const unsigned* dep = nullptr;
-    if (t == 0 && !exhausted) {
-      nxt = decode_work((long)nxt_raw, a.batch, a.lag, T1, T2);
-      dep = dep_counter<Cfg>(nxt, a, &dep_target);
-      if (dep) dep_seen = ld_acquire(dep);
-    }
+    FB_TRACE(1);
+    if (a.trace && blockIdx.x == 0 && t == 0 && k < kTraceTiles) a.trace[((long)g * (GT / 32) * kTraceTiles + k) * kTracePhases + 7] = wi.pass;
 
     // ---- staging -> registers; the staging buffer is free again as soon as every thread has its samples ----
     Tile f;
     if (wi.pass == 1) f.template load<false, C, 1>(t, stage_g);        // staging = [n1][C]
     else f.template load<true, 1, N2>(t, stage_g);                     // staging = C contiguous rows
     mbar_arrive(&ctl->empty);
-
-    bool pending = false;
-    if (t == 0) {
-      mbar_wait(&ctl->empty, k & 1);
-      if (wi.pass == 2) atomicAdd(&done2[wi.b], 1u);                   // ring slot consumed by this tile
-      if (!exhausted) {
-        if (!dep || dep_seen >= dep_target) {
-          if (dep) fence_proxy_async();
-          issue_tile<Cfg>(nxt, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
-          n_p1 += nxt.pass == 1;
-          exhausted = nxt.pass < 0;
-          if (!exhausted) nxt_raw = atomicAdd(queue, 1u);
-        } else {
-          pending = true;      // never block here: this group's own tile may be (part of) the dependency
-        }
-      }
+    if (wi.pass == 2 && (t & 31) == 0) {
+      // the last warp of the group to have pulled its samples reports the ring slot as consumed by this
+      // tile -- promptly and from the consumer side (a lazy report by the producer could deadlock it
+      // against its own dependency wait)
+      if (atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
     }
+    FB_TRACE(2);
 
     if (wi.pass == 1) f.template stage_a<false>(t, twa); else f.template stage_a<true>(t, twa);
 
@@ -317,37 +404,43 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       unsigned spins = 0;
       while (atomicCAS(lock, 0, 1) != 0) if (++spins > (1u << 26)) __trap();
     }
+    FB_TRACE(3);
     group_sync(bar_id, GT);
     if (wi.pass == 1) f.template scatter<false, Lay1>(t, exch); else f.template scatter<true, Lay2>(t, exch);
+    FB_TRACE(4);
     group_sync(bar_id, GT);
     if (wi.pass == 1) f.template gather<false, Lay1>(t, exch); else f.template gather<false, Lay2>(t, exch);
     group_sync(bar_id, GT);
     if (t == 0) { __threadfence_block(); atomicExch(lock, 0); }
+    FB_TRACE(5);
 
     // ---- stage B and the stores ---------------------------------------------------------------------------------
     f.stage_b();
     if (wi.pass == 1) {
       const V* tb = tab_g + (size_t)(k_p1 & 1) * 2 * C * R;
       ++k_p1;
-      V* dst = a.scratch + (size_t)(wi.b % a.ring) * N + (size_t)wi.tile * C;
+      V* dst = a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C;
       f.template store_factored<N2, 1, 2>(t, dst, tb, tb + C * R);       // intermediate: keep in L2
-      group_sync(bar_id, GT);
-      if (t == 0) { __threadfence(); red_release_add(&done1[wi.b], 1u); }
+      // report "stores issued"; the last warp of the group hands the tile to the signaller warp
+      __syncwarp();
+      if ((t & 31) == 0 && atom_add_acq_rel_cta_shared(&ctl->stored_warps, 1u) == GT / 32 - 1) {
+        ctl->stored_warps = 0;
+        for (unsigned spins = 0; k_p1 - ld_acquire_cta_shared(&ctl->acked) > (unsigned)kStoreRing; ++spins) {
+          if (spins > (1u << 24)) __trap();   // the signaller is more than kStoreRing tiles behind: wait
+          __nanosleep(100);
+        }
+        ctl->store_b[(k_p1 - 1) % kStoreRing] = wi.b;
+        st_release_cta_shared(&ctl->stored_seq, k_p1);
+      }
     } else {
       V* dst = a.out + (size_t)wi.b * N + (size_t)wi.tile * C;
       if (a.do_scale) f.template store<false, N1, 1, false, true, 1>(t, dst, nullptr, a.scale);   // streaming
       else f.template store<false, N1, 1, false, false, 1>(t, dst, nullptr, a.scale);
     }
-
-    if (t == 0 && pending) {
-      spin_until_ge(dep, dep_target);
-      fence_proxy_async();
-      issue_tile<Cfg>(nxt, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
-      n_p1 += nxt.pass == 1;
-      exhausted = nxt.pass < 0;
-      if (!exhausted) nxt_raw = atomicAdd(queue, 1u);
-    }
+    FB_TRACE(6);
   }
+  group_sync(bar_id, GT);
+  if (t == 0) st_release_cta_shared(&ctl->finished, 1u);
 }
 
 }  // namespace fused

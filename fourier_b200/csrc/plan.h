@@ -120,7 +120,7 @@ class Plan {
   size_t chunk_ = 0;                 // transforms per L2-resident chunk (two-pass)
   const void* fused_ops_ = nullptr;  // FusedOps<T>: persistent single-launch variant
   int ring_ = 0, lag_ = 0, sm_count_ = 148;
-  DeviceBuffer counters_, tbase_, tstep_;
+  DeviceBuffer counters_, tbase_, tstep_, trace_;
 
   // kBluestein*: chirp x[i] (N entries), W = FFT_M(wrapped chirp) (M entries), both forward;
   // the inverse direction uses their conjugate-symmetric counterparts computed at plan time.

@@ -13,6 +13,7 @@
 // chunking in exec_twopass() arranges.  All global accesses are >= 128-byte contiguous pieces:
 //   pass 1 reads  x  as C consecutive columns (C*8 B per row),  writes A[k1][n2] the same way;
 //   pass 2 reads  A  as whole contiguous rows,                  writes X as C consecutive k1.
+#include <cstdio>
 #include <cstdlib>
 
 #include "plan.h"
@@ -97,11 +98,11 @@ template <class Cfg> struct FusedImpl {
 
 template <typename T> const FusedOps<T>* fused_lookup(size_t n);
 template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
-  if (n == ((size_t)1 << 20)) return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8>>::ops(6, 3);
+  if (n == ((size_t)1 << 20)) return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8>>::ops(8, 4);
   return nullptr;
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
-  if (n == ((size_t)1 << 16)) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4>>::ops(48, 24);
+  if (n == ((size_t)1 << 16)) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4>>::ops(64, 32);
   return nullptr;
 }
 
@@ -158,6 +159,7 @@ cudaError_t Plan<T>::init_twopass() {
       FB_CHECK((upload_vec<T, cpx<T>>(tstep_, ts)));
       fused_ops_ = f;
       ring_ = std::max(2, env_int("FOURIER_B200_RING", f->default_ring));
+      while (ring_ & (ring_ - 1)) ++ring_;   // the kernel wants a power of two
       lag_ = std::min(ring_ - 1, std::max(1, env_int("FOURIER_B200_LAG", f->default_lag)));
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
@@ -178,7 +180,8 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
   else if (do_scale) scale = (T)1 / std::sqrt((T)n_);
   if (fused_ops_ && batch <= (size_t)1 << 24) {
     const auto* f = static_cast<const FusedOps<T>*>(fused_ops_);
-    const int ring = (int)std::min<size_t>((size_t)ring_, std::max<size_t>(batch, 2));
+    int ring = ring_;
+    while (ring > 2 && (size_t)ring / 2 >= batch) ring /= 2;
     const int lag = std::min(lag_, ring - 1);
     FB_CHECK(work_.reserve((size_t)ring * n_ * sizeof(C)));
     const size_t cbytes = (1 + 2 * batch) * sizeof(unsigned);
@@ -189,11 +192,31 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
     a.twa = (const TwPair<T>*)tw_a_.data();
     a.tbase = (const C*)tbase_.data(); a.tstep = (const C*)tstep_.data();
     a.counters = (unsigned*)counters_.data();
+    a.trace = nullptr;
+    if (std::getenv("FOURIER_B200_TRACE")) {
+      const size_t tbytes = sizeof(long long) * 64 * fused::kTraceTiles * fused::kTracePhases;
+      FB_CHECK(trace_.reserve(tbytes));
+      FB_CHECK(cudaMemsetAsync(trace_.data(), 0, tbytes, s));
+      a.trace = (long long*)trace_.data();
+    }
     a.batch = (int)batch; a.ring = ring; a.lag = lag; a.scale = scale; a.do_scale = do_scale ? 1 : 0;
     const size_t tiles = batch * (n1_ + n2_) / 8;
     const int grid = (int)std::min<size_t>((size_t)sm_count_, std::max<size_t>(1, tiles / 2));
     FB_CHECK(f->launch(a, fwd, grid, s));
     launches_ += 1;
+    if (a.trace) {  // dump the timeline of CTA 0 (debug aid; synchronises)
+      std::vector<long long> h(64 * fused::kTraceTiles * fused::kTracePhases);
+      FB_CHECK(cudaStreamSynchronize(s));
+      FB_CHECK(cudaMemcpy(h.data(), trace_.data(), h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      if (FILE* fp = fopen(std::getenv("FOURIER_B200_TRACE"), "w")) {
+        for (int w = 0; w < 20; ++w)
+          for (int k = 0; k < fused::kTraceTiles; ++k) {
+            const long long* r = &h[((size_t)w * fused::kTraceTiles + k) * fused::kTracePhases];
+            fprintf(fp, "%d %d %lld %lld %lld %lld %lld %lld %lld %lld\n", w, k, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+          }
+        fclose(fp);
+      }
+    }
     return cudaSuccess;
   }
   const size_t chunk = std::min(chunk_, batch);
