@@ -37,6 +37,15 @@ WORKLOADS = {
 BYTES_PER_SAMPLE = {"f32": 16, "f64": 32}  # algorithmic: read once + write once
 
 
+def measured_traffic(workload):
+    """DRAM bytes per sample of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)[workload]
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -106,7 +115,7 @@ def cpu_baseline(n, real, seconds_target=12.0, threads=None):
     # probe one transform per thread, then size the sample for ~seconds_target of CPU work
     x = O.fill_input(threads, n, dt)
     _, sec = O.transform_batch(x, O.FFT, threads)
-    per_thread = max(1, min(int(seconds_target / max(sec, 1e-6)), max(1, (1 << 28) // (n * threads))))
+    per_thread = max(1, min(int(seconds_target / max(sec, 1e-6)), max(1, (1 << 31) // (n * threads))))
     batch = per_thread * threads
     x = O.fill_input(batch, n, dt)
     _, sec = O.transform_batch(x, O.FFT, threads)
@@ -270,6 +279,8 @@ def main():
     peak, peak_src = measured_peak()
     bps = BYTES_PER_SAMPLE[real]
     achieved = batch * n * bps / (ms_per_step * 1e-3) / 1e9  # per GPU
+    tr = measured_traffic(args.workload)
+    one_kernel = int(launches_per_step) == 1
     out = {
         "metric": "batched 1D FFT complex-samples/sec", "value": value, "unit": "complex samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -280,9 +291,14 @@ def main():
                    else "inputs smaller than L2: numbers are L2-warm",
                    "parallelism": f"batch-sharded x{world}, no collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "traffic": (tr["dram_bytes_per_sample"] * batch * n) if tr else None,
+                     "traffic_source": tr["source"] if tr else None,
+                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_sample": bps,
-                     "kernel": "whole step (all launches of one batched transform)"},
+                     "algorithmic_bytes_per_launch": batch * n * bps,
+                     "kernel": (tr["kernel"] if tr else "fused two-pass kernel") + " -- one launch = one step (whole batch)"
+                     if one_kernel else "whole step (all launches of one batched transform)",
+                     "launch_ms": ms_per_step},
         "gpu_launches": int(launches_per_step) * args.steps,
         "clocks": clocks.summary(),
         "verify": verify,
