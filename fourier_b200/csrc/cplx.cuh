@@ -16,6 +16,10 @@
 #include "twiddle_consts.h"
 
 #define FB_HD __host__ __device__ __forceinline__
+// The compile-time loops below run generic lambdas; if the inliner's budget runs out in a large
+// translation unit a lambda becomes a real call, its by-reference capture of the register array forces
+// that array into local memory (seen as a 296-byte stack frame in one kernel).  Never let that happen.
+#define FB_LAMBDA __attribute__((always_inline))
 
 namespace fb200 {
 
@@ -128,7 +132,7 @@ template <int LEN, int BASE, bool FWD, typename T, int TOTAL>
 FB_HD void dif2(cpx<T> (&x)[TOTAL]) {
   if constexpr (LEN >= 2) {
     constexpr int H = LEN / 2;
-    static_for<0, H>([&](auto J) {
+    static_for<0, H>([&](auto J) FB_LAMBDA {
       constexpr int j = decltype(J)::value;
       cpx<T> a = x[BASE + j], b = x[BASE + j + H];
       x[BASE + j] = cadd(a, b);

@@ -185,18 +185,17 @@ cudaError_t Plan<T>::init_global_stages() {
 template <typename T>
 cudaError_t Plan<T>::init_bluestein(bool allow_fast_paths) {
   m_ = bluestein_inner_size(n_);
-  inner_.reset(Plan<T>::create(m_, device_, allow_fast_paths));
-  if (!inner_) return cudaErrorUnknown;
 
   // chirp[i] = exp(-i*pi*i^2/N) = w_{2N}^{i^2 mod 2N}.  The reference forms i^2 in f64 without the
   // reduction (bluesteins.rs:31,33,57), which costs accuracy for large N; reducing first is exact.
   std::vector<cpx<T>> chirp(n_);
-  std::vector<double> wr(m_, 0.0), wi(m_, 0.0);
+  std::vector<double> wr(m_, 0.0), wi(m_, 0.0), cr(n_), ci(n_);
   for (size_t i = 0; i < n_; ++i) {
     const size_t idx = (size_t)(((unsigned __int128)i * i) % (2 * (unsigned __int128)n_));
     double re, im;
     host_twiddle(idx, 2 * n_, &re, &im);
     chirp[i] = mk<T>((T)re, (T)im);
+    cr[i] = re; ci[i] = im;
     // wrapped conjugate chirp (bluesteins.rs:18-45): w[i] = w[M-i] = exp(+i*pi*i^2/N)
     wr[i] = re; wi[i] = -im;
     if (i != 0) { wr[m_ - i] = re; wi[m_ - i] = -im; }
@@ -206,6 +205,13 @@ cudaError_t Plan<T>::init_bluestein(bool allow_fast_paths) {
   host_fft_pow2(wr, wi, false);
   std::vector<cpx<T>> wf(m_);
   for (size_t i = 0; i < m_; ++i) wf[i] = mk<T>((T)wr[i], (T)wi[i]);
+  if (allow_fast_paths && init_bluestein_fused(cr, ci, wr, wi) == cudaSuccess) {
+    inner_.reset();   // the fused kernel carries its own on-chip inner FFTs
+    path_ = Path::kBluesteinFused;
+    return cudaSuccess;
+  }
+  inner_.reset(Plan<T>::create(m_, device_, allow_fast_paths));
+  if (!inner_) return cudaErrorUnknown;
   FB_CHECK(upload<T>(chirp_, chirp));
   FB_CHECK(upload<T>(wf_, wf));
   path_ = Path::kBluestein;

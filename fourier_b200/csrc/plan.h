@@ -103,6 +103,8 @@ class Plan {
   cudaError_t init_onchip();
   cudaError_t init_twopass();
   cudaError_t init_bluestein(bool allow_fast_paths);
+  cudaError_t init_bluestein_fused(const std::vector<double>& chirp_re, const std::vector<double>& chirp_im,
+                                   const std::vector<double>& w_re, const std::vector<double>& w_im);
 
   size_t n_ = 0;
   int device_ = 0;

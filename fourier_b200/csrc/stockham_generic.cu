@@ -43,7 +43,7 @@ stockham_stage_kernel(const cpx<T>* __restrict__ in, cpx<T>* __restrict__ out,
       for (int k = 0; k < R; ++k) y[k] = x[k];
     } else {
       dft_pow2<R, FWD, T>(x);
-      static_for<0, R>([&](auto K) {
+      static_for<0, R>([&](auto K) FB_LAMBDA {
         constexpr int k = decltype(K)::value;
         y[k] = x[rev<R>(k)];
       });

@@ -101,11 +101,11 @@ struct TileFFT {
   // DFT_RA over i for each owned j, then the stage twiddle w_L^{j*p} (skipped for p == 0).
   template <bool UF> FB_HD void stage_a(int t, const TwPair<T>* __restrict__ twa) {
     const int u = u_of<UF>(t);
-    static_for<0, NA>([&](auto A) {
+    static_for<0, NA>([&](auto A) FB_LAMBDA {
       constexpr int a = decltype(A)::value;
       dif2<RA, a * RA, FWD, T, E>(v);
       const int j = u + TP * a;
-      static_for<0, RA / 2>([&](auto H) {
+      static_for<0, RA / 2>([&](auto H) FB_LAMBDA {
         constexpr int h = decltype(H)::value;
         const TwPair<T> w = twa[twa_index<RA, RB>(j, h)];
         if constexpr (h != 0) v[a * RA + bitrev(2 * h, ilog2(RA))] = ctw<FWD>(v[a * RA + bitrev(2 * h, ilog2(RA))], w.a);
@@ -118,10 +118,10 @@ struct TileFFT {
   template <bool UF, class LAY> FB_HD void scatter(int t, V* smem) const {
     constexpr int SJ = LAY::SJ, SP = LAY::SP, SC = LAY::SC;
     const int col = col_of<UF>(t), u = u_of<UF>(t);
-    static_for<0, NA>([&](auto A) {
+    static_for<0, NA>([&](auto A) FB_LAMBDA {
       constexpr int a = decltype(A)::value;
       V* s = smem + (u + TP * a) * SJ + col * SC;
-      static_for<0, RA>([&](auto P) {
+      static_for<0, RA>([&](auto P) FB_LAMBDA {
         constexpr int p = decltype(P)::value;
         s[p * SP] = v[a * RA + bitrev(p, ilog2(RA))];
       });
@@ -141,7 +141,7 @@ struct TileFFT {
   }
 
   FB_HD void stage_b() {
-    static_for<0, NB>([&](auto Cc) {
+    static_for<0, NB>([&](auto Cc) FB_LAMBDA {
       constexpr int c = decltype(Cc)::value;
       dif2<RB, c * RB, FWD, T, E>(v);
     });
@@ -153,7 +153,7 @@ struct TileFFT {
   template <bool UF, long KS, long CS, bool TW2, bool SCALE, int HINT = 0>
   FB_HD void store(int t, V* __restrict__ base, const V* __restrict__ tw2, T scale) const {
     const int col = col_of<UF>(t), u = u_of<UF>(t);
-    static_for<0, NB>([&](auto Cc) {
+    static_for<0, NB>([&](auto Cc) FB_LAMBDA {
       constexpr int c = decltype(Cc)::value;
       const long off = (long)col * CS + (long)(u + TP * c) * KS;
       if constexpr (TW2) {
@@ -163,14 +163,14 @@ struct TileFFT {
         V w[TWB];
 #pragma unroll
         for (int q = 0; q < TWB; ++q) w[q] = tw2[off + (long)(RA * q) * KS];
-        static_for<0, RB / TWB>([&](auto G) {
+        static_for<0, RB / TWB>([&](auto G) FB_LAMBDA {
           constexpr int g = decltype(G)::value;
           V wn[TWB];
           if constexpr ((g + 1) * TWB < RB) {
 #pragma unroll
             for (int q = 0; q < TWB; ++q) wn[q] = tw2[off + (long)(RA * ((g + 1) * TWB + q)) * KS];
           }
-          static_for<0, TWB>([&](auto Q) {
+          static_for<0, TWB>([&](auto Q) FB_LAMBDA {
             constexpr int r = g * TWB + decltype(Q)::value;
             V val = ctw<FWD>(v[c * RB + bitrev(r, ilog2(RB))], w[decltype(Q)::value]);
             if constexpr (SCALE) val = cscale(val, scale);
@@ -182,7 +182,7 @@ struct TileFFT {
           }
         });
       } else {
-        static_for<0, RB>([&](auto Rr) {
+        static_for<0, RB>([&](auto Rr) FB_LAMBDA {
           constexpr int r = decltype(Rr)::value;
           V val = v[c * RB + bitrev(r, ilog2(RB))];
           if constexpr (SCALE) val = cscale(val, scale);
@@ -199,12 +199,12 @@ struct TileFFT {
   template <long KS, long CS, int HINT>
   FB_HD void store_factored(int t, V* __restrict__ base, const V* sbase, const V* sstep) const {
     const int col = col_of<false>(t), u = u_of<false>(t);
-    static_for<0, NB>([&](auto Cc) {
+    static_for<0, NB>([&](auto Cc) FB_LAMBDA {
       constexpr int c = decltype(Cc)::value;
       const int p = u + TP * c;
       const long off = (long)col * CS + (long)p * KS;
       const V wb = sbase[col * RA + p];
-      static_for<0, RB>([&](auto Rr) {
+      static_for<0, RB>([&](auto Rr) FB_LAMBDA {
         constexpr int r = decltype(Rr)::value;
         const V w = cmul(wb, sstep[r * C + col]);
         st_hint<HINT>(&base[off + (long)(RA * r) * KS], ctw<FWD>(v[c * RB + bitrev(r, ilog2(RB))], w));

@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "onchip_kernels.cuh"
 #include "twopass_kernels.cuh"
 
 using namespace fb200;
@@ -60,7 +61,7 @@ static void run_body(const typename Body::Args& a, long blocks) {
 }
 
 // Bank-conflict report for the exchange of a tile: scatter with mapping UF_A, gather with col-fast.
-template <class Tile, class LAY, bool UF_A>
+template <class Tile, class LAY, bool UF_A, bool UF_B = false>
 static void report_conflicts(const char* name) {
   using V = typename Tile::V;
   constexpr int B = (int)sizeof(V);
@@ -81,8 +82,8 @@ static void report_conflicts(const char* name) {
         std::vector<long> idx;
         for (int l = 0; l < 32; ++l) {
           const int t = warp * 32 + l;
-          idx.push_back((long)j * LAY::SJ + (long)(Tile::template u_of<false>(t) + Tile::TP * c) * LAY::SP +
-                        (long)Tile::template col_of<false>(t) * LAY::SC);
+          idx.push_back((long)j * LAY::SJ + (long)(Tile::template u_of<UF_B>(t) + Tile::TP * c) * LAY::SP +
+                        (long)Tile::template col_of<UF_B>(t) * LAY::SC);
         }
         worst_r = std::max(worst_r, conflict_degree<B>(idx));
       }
@@ -143,6 +144,121 @@ static int check(const char* name, double tol) {
   return bad;
 }
 
+// ---- on-chip kernels (onchip_kernels.cuh) -------------------------------------------------------------------------
+template <typename T, int RA, int RB, int E, int WARPS>
+static int check_onchip(const char* name, double tol) {
+  int bad = 0;
+  for (int fwd = 1; fwd >= 0; --fwd) {
+    const long L = RA * RB, batch = 5;   // 5 is not a multiple of the transforms per CTA: exercises the tail
+    std::vector<cpx<T>> x((size_t)L * batch), out((size_t)L * batch);
+    fill<T>(x, 21 + fwd);
+    auto twa = make_twa<T>(RA, RB);
+    auto run = [&](auto cfg_tag) {
+      using Cfg = decltype(cfg_tag);
+      using Body = onchip::FftBody<Cfg>;
+      typename Body::Args a = {x.data(), out.data(), twa.data(), batch, (T)0.5, 1};
+      std::vector<cpx<T>> smem(Cfg::Tile::template smem_elems<typename Cfg::Lay>());
+      std::vector<typename Cfg::Tile> thr(Cfg::THREADS);
+      const long groups = (batch + Cfg::C - 1) / Cfg::C;
+      for (long g = 0; g < groups; ++g) {
+        for (int t = 0; t < Cfg::THREADS; ++t) Body::phase1(thr[t], a, g, t, smem.data(), twa.data());
+        for (int t = 0; t < Cfg::THREADS; ++t) Body::phase2(thr[t], a, g, t, smem.data());
+      }
+      report_conflicts<typename Cfg::Tile, typename Cfg::Lay, true, true>("exchange");
+    };
+    if (fwd) run(onchip::OnChipCfg<T, RA, RB, E, WARPS, true>{}); else run(onchip::OnChipCfg<T, RA, RB, E, WARPS, false>{});
+    double worst = 0;
+    for (long b = 0; b < batch; ++b) {
+      std::vector<double> re(L), im(L);
+      for (long i = 0; i < L; ++i) { re[i] = x[b * L + i].x; im[i] = x[b * L + i].y; }
+      host_fft_pow2(re, im, !fwd);
+      double mr = 0, me = 0;
+      for (long i = 0; i < L; ++i) {
+        mr = std::max(mr, std::hypot(re[i], im[i]) * 0.5);
+        me = std::max(me, std::hypot(out[b * L + i].x - 0.5 * re[i], out[b * L + i].y - 0.5 * im[i]));
+      }
+      worst = std::max(worst, me / mr);
+    }
+    printf("%s L=%d %s: max rel err %.3e %s\n", name, RA * RB, fwd ? "forward" : "inverse", worst, worst < tol ? "OK" : "FAIL");
+    bad += !(worst < tol);
+  }
+  return bad;
+}
+
+template <typename T, int R, int WARPS>
+static int check_bluestein(const char* name, long n, double tol) {
+  using Cfg = onchip::OnChipCfg<T, R, R, R, WARPS, true>;
+  using Body = onchip::BluesteinBody<Cfg>;
+  using V = cpx<T>;
+  const long L = R * R, M = 2 * L, batch = 3;
+  int bad = 0;
+  for (int inverse = 0; inverse < 2; ++inverse) {
+    // tables exactly as Plan<T>::init_bluestein / init_bluestein_fused build them
+    std::vector<double> cr(n), ci(n), wr(M, 0.0), wi(M, 0.0);
+    for (long i = 0; i < n; ++i) {
+      const size_t idx = (size_t)(((unsigned __int128)i * i) % (2 * (unsigned __int128)n));
+      host_twiddle(idx, 2 * n, &cr[i], &ci[i]);
+      wr[i] = cr[i]; wi[i] = -ci[i];
+      if (i) { wr[M - i] = cr[i]; wi[M - i] = -ci[i]; }
+    }
+    host_fft_pow2(wr, wi, false);
+    const double sgn = inverse ? -1.0 : 1.0;
+    std::vector<V> chirp(L, mk<T>(0, 0)), wm(L), wce(L), wco(L);
+    for (long i = 0; i < L; ++i) {
+      if (i < n) chirp[i] = mk<T>((T)cr[i], (T)(sgn * ci[i]));
+      double re, im;
+      host_twiddle(i, M, &re, &im);
+      wm[i] = mk<T>((T)re, (T)im);
+      wce[i] = mk<T>((T)wr[2 * i], (T)(-sgn * wi[2 * i]));
+      wco[i] = mk<T>((T)wr[2 * i + 1], (T)(-sgn * wi[2 * i + 1]));
+    }
+    auto twa = make_twa<T>(R, R);
+    std::vector<V> x((size_t)n * batch), out((size_t)n * batch);
+    fill<T>(x, 31 + inverse);
+    typename Body::Args a = {x.data(), out.data(), twa.data(), chirp.data(), wm.data(), wce.data(), wco.data(), n, batch,
+                             (T)(1.0 / M)};
+    std::vector<V> exch(Cfg::Tile::template smem_elems<typename Cfg::Lay>());
+    std::vector<V> stash((size_t)R * Cfg::THREADS);
+    std::vector<typename Cfg::Tile> thr(Cfg::THREADS);
+    const long groups = (batch + Cfg::C - 1) / Cfg::C;
+    auto all = [&](auto fn) { for (int t = 0; t < Cfg::THREADS; ++t) fn(t); };
+    for (long g = 0; g < groups; ++g) {
+      auto bidx = [&](int t) { long b = g * Cfg::C + Cfg::Tile::template col_of<true>(t); return b; };
+      auto bcl = [&](int t) { long b = bidx(t); return b < batch ? b : batch - 1; };
+      for (int odd = 0; odd < 2; ++odd) {
+        all([&](int t) { if (odd) Body::template load_half<true>(thr[t], a, bcl(t), t, exch.data(), twa.data(), chirp.data(), wm.data());
+                         else Body::template load_half<false>(thr[t], a, bcl(t), t, exch.data(), twa.data(), chirp.data(), wm.data()); });
+        all([&](int t) { Body::middle(thr[t], t, exch.data(), odd ? wco.data() : wce.data()); });
+        all([&](int t) { Body::second_fft_start(thr[t], t, exch.data(), twa.data()); });
+        all([&](int t) { Body::second_fft_finish(thr[t], t, exch.data()); });
+        if (!odd) all([&](int t) { Body::stash_even(thr[t], t, stash.data()); });
+      }
+      all([&](int t) { if (bidx(t) < batch) Body::combine_store(stash.data(), thr[t], a, bcl(t), t, chirp.data(), wm.data()); });
+    }
+    double worst = 0;
+    for (long b = 0; b < batch; ++b) {
+      double mr = 0, me = 0;
+      for (long k = 0; k < n; ++k) {
+        double sr = 0, si = 0;
+        for (long j = 0; j < n; ++j) {
+          double re, im;
+          host_twiddle((size_t)((k * j) % n), (size_t)n, &re, &im);
+          if (inverse) im = -im;
+          sr += x[b * n + j].x * re - x[b * n + j].y * im;
+          si += x[b * n + j].x * im + x[b * n + j].y * re;
+        }
+        mr = std::max(mr, std::hypot(sr, si));
+        me = std::max(me, std::hypot(out[b * n + k].x - sr, out[b * n + k].y - si));
+      }
+      worst = std::max(worst, me / mr);
+    }
+    printf("%s N=%ld (L=%ld) %s: max rel err vs naive f64 DFT %.3e %s\n", name, n, L, inverse ? "inverse" : "forward", worst,
+           worst < tol ? "OK" : "FAIL");
+    bad += !(worst < tol);
+  }
+  return bad;
+}
+
 int main() {
   int bad = 0;
   bad += check<float, TwoPass<float, 32, 32, 8, 8, 8, 2, 2>>("f32 2^20 (C=8)", 2e-6);
@@ -152,6 +268,20 @@ int main() {
   bad += check<double, TwoPass<double, 16, 16, 8, 8, 4, 2, 2>>("f64 2^16", 5e-15);
   bad += check<double, TwoPass<double, 8, 8, 16, 16, 0, 4, 4>>("f64 2^12", 5e-15);
   bad += check<double, TwoPass<double, 8, 16, 16, 8, 0, 4, 2>>("f64 2^14", 5e-15);
+  bad += check_onchip<float, 8, 8, 8, 8>("onchip f32", 2e-6);
+  bad += check_onchip<float, 8, 16, 16, 8>("onchip f32", 2e-6);
+  bad += check_onchip<float, 16, 16, 16, 8>("onchip f32", 2e-6);
+  bad += check_onchip<float, 16, 32, 32, 8>("onchip f32", 2e-6);
+  bad += check_onchip<float, 32, 32, 32, 8>("onchip f32", 2e-6);
+  bad += check_onchip<double, 8, 8, 8, 8>("onchip f64", 5e-15);
+  bad += check_onchip<double, 8, 16, 16, 8>("onchip f64", 5e-15);
+  bad += check_onchip<double, 16, 16, 16, 8>("onchip f64", 5e-15);
+  bad += check_bluestein<float, 32, 11>("bluestein f32", 1009, 3e-6);
+  bad += check_bluestein<float, 32, 11>("bluestein f32", 513, 3e-6);
+  bad += check_bluestein<float, 16, 8>("bluestein f32", 255, 3e-6);
+  bad += check_bluestein<float, 8, 8>("bluestein f32", 37, 3e-6);
+  bad += check_bluestein<double, 16, 8>("bluestein f64", 191, 1e-13);
+  bad += check_bluestein<double, 8, 8>("bluestein f64", 61, 1e-13);
   printf(bad ? "EMULATION FAILED (%d)\n" : "EMULATION OK\n", bad);
   return bad ? 1 : 0;
 }
