@@ -33,7 +33,8 @@ struct OnChipCfg {
   using Lay = WarpLayout<RA, RB>;
   static constexpr int L = RA * RB, TP = L / E, THREADS = WARPS * 32, C = THREADS / TP;
   static_assert(TP <= 32, "one FFT must fit inside a warp");
-  static constexpr size_t EX_BYTES = sizeof(cpx<T>) * (size_t)Tile::template smem_elems<Lay>();
+  // rounded up: the twiddle pairs behind it are read with 128-bit (f32) / 2 x 128-bit (f64) loads
+  static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * (size_t)Tile::template smem_elems<Lay>() + 127) / 128) * 128;
   static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (RA / 2) * RB;
 };
 
@@ -83,7 +84,7 @@ onchip_fft_kernel(const typename FftBody<Cfg>::Args a) {
   using Body = FftBody<Cfg>;
   using V = typename Cfg::Tile::V;
   using T = decltype(V::x);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   V* exch = reinterpret_cast<V*>(smem_raw);
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(smem_raw + Cfg::EX_BYTES);
   for (int i = threadIdx.x; i < (Cfg::Tile::RA / 2) * Cfg::Tile::RB; i += Cfg::THREADS) twa[i] = a.twa[i];
@@ -209,7 +210,7 @@ bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
   using V = typename Cfg::Tile::V;
   using T = decltype(V::x);
   constexpr int L = Cfg::L;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   V* exch = reinterpret_cast<V*>(smem_raw);
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(smem_raw + Cfg::EX_BYTES);
   V* tabs = reinterpret_cast<V*>(smem_raw + Cfg::EX_BYTES + Cfg::TWA_BYTES);
