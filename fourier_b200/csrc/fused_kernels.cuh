@@ -154,23 +154,24 @@ template <typename T> struct FusedArgs {
 };
 
 // Configuration: N = (R*R)^2, tiles of C FFTs, G consumer groups per CTA.
-template <typename T_, int R_, int C_, int G_, int PAD1_>
+template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1>
 struct FusedCfg {
   using T = T_;
-  static constexpr int R = R_, C = C_, G = G_;
+  static constexpr int R = R_, C = C_, G = G_, EXB = EXB_;   // EXB exchange buffers: group g uses g % EXB
   static constexpr long L = (long)R * R, N1 = L, N2 = L, N = N1 * N2;
   template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
   using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
   using Lay2 = ExLayout<R * C + 1, C, 1>;                          // pass 2: scatter u-fast, gather col-fast
   static constexpr int GT = R * C;                    // threads per group
   static constexpr int CONSUMERS = G * GT;
-  static constexpr int THREADS = CONSUMERS + 128;     // + one producer warpgroup (one lane of it works)
+  static constexpr int AUX = ((G + 1 + 3) / 4) * 128;  // G producer warps + 1 signaller warp, in whole warpgroups
+  static constexpr int THREADS = CONSUMERS + AUX;
   // Register budget.  Registers are handed out per 4 warps, so a 17th warp costs as much as 4; the
   // producer warpgroup therefore gives its registers back (setmaxnreg.dec) and the consumers take
   // them (setmaxnreg.inc): LAUNCH_REGS per thread at launch, REGS_CONSUMER / REGS_PRODUCER afterwards.
   static constexpr int LAUNCH_REGS = ((65536 / THREADS) / 8) * 8;
   static constexpr int REGS_PRODUCER = 24;
-  static constexpr int REGS_CONSUMER_RAW = ((LAUNCH_REGS * THREADS - REGS_PRODUCER * 128) / CONSUMERS / 8) * 8;
+  static constexpr int REGS_CONSUMER_RAW = ((LAUNCH_REGS * THREADS - REGS_PRODUCER * AUX) / CONSUMERS / 8) * 8;
   static constexpr int REGS_CONSUMER = REGS_CONSUMER_RAW > 232 ? 232 : REGS_CONSUMER_RAW;
   static constexpr int T1 = (int)(N2 / C), T2 = (int)(N1 / C);
   static constexpr uint32_t TILE_BYTES = (uint32_t)(sizeof(cpx<T>) * C * L);
@@ -181,7 +182,7 @@ struct FusedCfg {
   static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (R / 2) * R;
   // layout: staging[G] | exchange | twa | tile tables [G][2 bufs][base, step] | control
   static constexpr size_t OFF_EX = (size_t)G * TILE_BYTES;
-  static constexpr size_t OFF_TWA = OFF_EX + EX_BYTES;
+  static constexpr size_t OFF_TWA = OFF_EX + (size_t)EXB * EX_BYTES;
   static constexpr size_t OFF_TAB = OFF_TWA + TWA_BYTES;
   static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 4 * TAB_BYTES;
   static constexpr size_t SMEM_BYTES = OFF_CTL + 512 /* control block: G * sizeof(GroupCtl) + lock */;
@@ -275,11 +276,11 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw;
   V* staging = reinterpret_cast<V*>(base);                                   // [G][C*L]
-  V* exch = reinterpret_cast<V*>(base + Cfg::OFF_EX);
+  unsigned char* exch_pool = base + Cfg::OFF_EX;
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
   V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][2][2][C*R]
   GroupCtl* ctl_all = reinterpret_cast<GroupCtl*>(base + Cfg::OFF_CTL);
-  int* lock = reinterpret_cast<int*>(ctl_all + G);
+  int* locks = reinterpret_cast<int*>(ctl_all + G);   // one per exchange buffer
 
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -292,7 +293,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       ctl_all[g].finished = 0;
       ctl_all[g].acked = 0;
     }
-    *lock = 0;
+    for (int i = 0; i < Cfg::EXB; ++i) locks[i] = 0;
     fence_barrier_init();
   }
   for (int i = tid; i < (R / 2) * R; i += Cfg::THREADS) twa[i] = a.twa[i];   // stage-A twiddles live in smem
@@ -374,6 +375,9 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   V* tab_g = tabs + (size_t)g * 4 * C * R;
   GroupCtl* ctl = &ctl_all[g];
   const int bar_id = 1 + g;
+  V* exch = reinterpret_cast<V*>(exch_pool + (size_t)(g % Cfg::EXB) * Cfg::EX_BYTES);
+  int* lock = &locks[g % Cfg::EXB];
+  constexpr bool kLocked = Cfg::EXB < G;   // several groups share one exchange buffer
   uint32_t k_p1 = 0;   // pass-1 tiles consumed so far by this group: selects the tile-table buffer
 
   for (uint32_t k = 0;; ++k) {
@@ -409,7 +413,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     if (wi.pass == 1) f.template stage_a<false>(t, twa); else f.template stage_a<true>(t, twa);
 
     // ---- exchange through the shared buffer, under the CTA-wide lock -----------------------------------------
-    if (t == 0) {
+    if (kLocked && t == 0) {
       unsigned spins = 0;
       while (atomicCAS(lock, 0, 1) != 0) if (++spins > (1u << 26)) __trap();
     }
@@ -420,7 +424,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     group_sync(bar_id, GT);
     if (wi.pass == 1) f.template gather<false, Lay1>(t, exch); else f.template gather<false, Lay2>(t, exch);
     group_sync(bar_id, GT);
-    if (t == 0) { __threadfence_block(); atomicExch(lock, 0); }
+    if (kLocked && t == 0) { __threadfence_block(); atomicExch(lock, 0); }
     FB_TRACE(5);
 
     // ---- stage B and the stores ---------------------------------------------------------------------------------

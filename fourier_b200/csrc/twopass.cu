@@ -51,6 +51,11 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
+int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <typename T> struct FusedOps {
   size_t n1, n2;
   int ra, rb, tile_c;
@@ -98,17 +103,17 @@ template <class Cfg> struct FusedImpl {
 
 template <typename T> const FusedOps<T>* fused_lookup(size_t n);
 template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
-  if (n == ((size_t)1 << 20)) return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8>>::ops(8, 4);
+  if (n == ((size_t)1 << 20)) {
+    // FOURIER_B200_TILE=4: four 128-thread groups on 4-column tiles (one warp of each group per SM
+    // sub-partition), two exchange buffers; default: two 256-thread groups on 8-column tiles
+    if (env_int("FOURIER_B200_TILE", 8) == 4) return FusedImpl<fused::FusedCfg<float, 32, 4, 4, 4, 2>>::ops(8, 4);
+    return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
+  }
   return nullptr;
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
-  if (n == ((size_t)1 << 16)) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4>>::ops(64, 32);
+  if (n == ((size_t)1 << 16)) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
   return nullptr;
-}
-
-int env_int(const char* name, int dflt) {
-  const char* e = std::getenv(name);
-  return e ? atoi(e) : dflt;
 }
 
 }  // namespace
@@ -200,7 +205,7 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
       a.trace = (long long*)trace_.data();
     }
     a.batch = (int)batch; a.ring = ring; a.lag = lag; a.scale = scale; a.do_scale = do_scale ? 1 : 0;
-    const size_t tiles = batch * (n1_ + n2_) / 8;
+    const size_t tiles = batch * (n1_ + n2_) / (size_t)f->tile_c;
     const int grid = (int)std::min<size_t>((size_t)sm_count_, std::max<size_t>(1, tiles / 2));
     FB_CHECK(f->launch(a, fwd, grid, s));
     launches_ += 1;
