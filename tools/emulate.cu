@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "fused_kernels.cuh"
 #include "onchip_kernels.cuh"
 #include "twopass_kernels.cuh"
 
@@ -259,6 +260,45 @@ static int check_bluestein(const char* name, long n, double tol) {
   return bad;
 }
 
+// ---- work queue of the fused kernel: order and dependency properties ---------------------------------------------
+static int check_queue() {
+  int bad = 0;
+  const int t1 = 128, t2 = 128;
+  for (int batch : {1, 2, 3, 5, 8, 17, 64}) {
+    for (int lag : {1, 2, 3, 4, 7}) {
+      for (int ring : {lag + 1, 2 * lag + 2}) {
+        const long total = (long)batch * (t1 + t2);
+        std::vector<long> pos1((size_t)batch * t1, -1), pos2((size_t)batch * t2, -1);
+        bool ok = true;
+        for (long w = 0; w < total; ++w) {
+          const fused::WorkItem it = fused::decode_work(w, batch, lag, t1, t2);
+          if (it.pass == 1 && it.b >= 0 && it.b < batch && it.tile >= 0 && it.tile < t1 && pos1[(size_t)it.b * t1 + it.tile] < 0)
+            pos1[(size_t)it.b * t1 + it.tile] = w;
+          else if (it.pass == 2 && it.b >= 0 && it.b < batch && it.tile >= 0 && it.tile < t2 && pos2[(size_t)it.b * t2 + it.tile] < 0)
+            pos2[(size_t)it.b * t2 + it.tile] = w;
+          else ok = false;   // out of range or duplicate
+        }
+        ok = ok && fused::decode_work(total, batch, lag, t1, t2).pass < 0;   // exhausted marker
+        for (int b = 0; b < batch && ok; ++b) {
+          long last1 = 0, first2 = total, last2 = 0, first1 = total;
+          for (int t = 0; t < t1; ++t) { last1 = std::max(last1, pos1[(size_t)b * t1 + t]); first1 = std::min(first1, pos1[(size_t)b * t1 + t]); }
+          for (int t = 0; t < t2; ++t) { first2 = std::min(first2, pos2[(size_t)b * t2 + t]); last2 = std::max(last2, pos2[(size_t)b * t2 + t]); }
+          if (first1 < 0 || first2 < 0) ok = false;                     // every tile appears
+          if (!(last1 < first2)) ok = false;                            // pass 2 of b only depends on earlier items
+          if (b + ring < batch) {                                       // slot reuse: pass 1 of b+ring after pass 2 of b
+            long f = total;
+            for (int t = 0; t < t1; ++t) f = std::min(f, pos1[(size_t)(b + ring) * t1 + t]);
+            if (!(last2 < f)) ok = false;
+          }
+        }
+        if (!ok) { printf("queue order FAILED batch=%d lag=%d ring=%d\n", batch, lag, ring); ++bad; }
+      }
+    }
+  }
+  printf("fused work queue: permutation / dependency-order properties %s\n", bad ? "FAILED" : "OK");
+  return bad;
+}
+
 int main() {
   int bad = 0;
   bad += check<float, TwoPass<float, 32, 32, 8, 8, 8, 2, 2>>("f32 2^20 (C=8)", 2e-6);
@@ -282,6 +322,7 @@ int main() {
   bad += check_bluestein<float, 8, 8>("bluestein f32", 37, 3e-6);
   bad += check_bluestein<double, 16, 8>("bluestein f64", 191, 1e-13);
   bad += check_bluestein<double, 8, 8>("bluestein f64", 61, 1e-13);
+  bad += check_queue();
   printf(bad ? "EMULATION FAILED (%d)\n" : "EMULATION OK\n", bad);
   return bad ? 1 : 0;
 }
