@@ -59,6 +59,7 @@ def test_soname_matches_reference_packaging():
 @pytest.mark.parametrize("src,cc,flags", [
     ("dropin_test.c", "gcc", ["-std=c11"]),
     ("dropin_test.cpp", "g++", ["-std=c++11"]),
+    ("trait_mirror_test.cpp", "g++", ["-std=c++11"]),
 ])
 def test_dropin_programs_compile_and_link(tmp_path, libfourier, src, cc, flags):
     exe = tmp_path / "a.out"

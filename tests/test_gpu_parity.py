@@ -250,7 +250,8 @@ def test_properties_at_baseline_sizes(real, n, batch):
 # ---- the drop-in programs, run against libfourier.so on the GPU box ------------------------------------------
 
 @pytest.mark.parametrize("src,cc,flags", [("dropin_test.c", "gcc", ["-std=c11"]),
-                                          ("dropin_test.cpp", "g++", ["-std=c++11"])])
+                                          ("dropin_test.cpp", "g++", ["-std=c++11"]),
+                                          ("trait_mirror_test.cpp", "g++", ["-std=c++11"])])
 def test_dropin_programs_run(tmp_path, src, cc, flags):
     libdir = os.path.join(ROOT, "fourier_b200", "lib")
     exe = tmp_path / "dropin"
