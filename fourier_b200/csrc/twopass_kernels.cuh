@@ -66,16 +66,24 @@ template <typename T> struct TwoPassOps {
   cudaError_t (*prepare)();
 };
 
-// Configuration of one supported size: both passes use R x R register stages.
-template <typename T, int R1, int R2, int C1, int C2, int PAD1, int MINB1, int MINB2>
-struct TwoPass {
-  static constexpr long N1 = (long)R1 * R1, N2 = (long)R2 * R2, N = N1 * N2;
+// Shape of one pass: length L = RA*RB, E samples per thread, C FFTs per tile, PAD = padding of the
+// exchange row (chosen so that the scatter is bank-conflict free; checked by tools/emulate.cu).
+template <int RA_, int RB_, int E_, int C_, int PAD_> struct Shape {
+  static constexpr int RA = RA_, RB = RB_, E = E_, C = C_, PAD = PAD_;
+  static constexpr long L = (long)RA * RB;
+};
+
+// Configuration of one supported size N = N1*N2: pass 1 = column tiles of shape S1, pass 2 = row tiles S2.
+template <typename T, class S1, class S2, int MINB1, int MINB2>
+struct TwoPassG {
+  static constexpr long N1 = S1::L, N2 = S2::L, N = N1 * N2;
+  static constexpr int C1 = S1::C, C2 = S2::C;
   // pass 1: FFT length N1 over n1 (stride N2), C1 adjacent columns; both stages "col fast"
-  template <bool FWD> using Tile1 = TileFFT<T, R1, R1, R1, C1, FWD>;
-  using Lay1 = ExLayout<R1 * C1 + PAD1, C1, 1>;
+  template <bool FWD> using Tile1 = TileFFT<T, S1::RA, S1::RB, S1::E, C1, FWD>;
+  using Lay1 = ExLayout<S1::RA * C1 + S1::PAD, C1, 1>;
   // pass 2: FFT length N2 over contiguous rows, C2 adjacent rows; stage A "u fast", stage B "col fast"
-  template <bool FWD> using Tile2 = TileFFT<T, R2, R2, R2, C2, FWD>;
-  using Lay2 = ExLayout<R2 * C2 + 1, C2, 1>;
+  template <bool FWD> using Tile2 = TileFFT<T, S2::RA, S2::RB, S2::E, C2, FWD>;
+  using Lay2 = ExLayout<S2::RA * C2 + S2::PAD, C2, 1>;
   template <bool FWD> using Body1 = TileBody<Tile1<FWD>, Lay1, N2, 1, false, N2, 1, true>;
   template <bool FWD> using Body2 = TileBody<Tile2<FWD>, Lay2, 1, N2, true, N1, 1, false>;
   template <bool FWD> static constexpr auto k1() {
@@ -120,10 +128,14 @@ struct TwoPass {
     return cudaGetLastError();
   }
   static const TwoPassOps<T>* ops() {
-    static const TwoPassOps<T> o = {(size_t)N1, (size_t)N2, R1, R1, R2, R2, &pass1, &pass2, &prepare};
+    static const TwoPassOps<T> o = {(size_t)N1, (size_t)N2, S1::RA, S1::RB, S2::RA, S2::RB, &pass1, &pass2, &prepare};
     return &o;
   }
 };
+
+// square shorthand used by the original configurations: both passes R x R register stages
+template <typename T, int R1, int R2, int C1, int C2, int PAD1, int MINB1, int MINB2>
+using TwoPass = TwoPassG<T, Shape<R1, R1, R1, C1, PAD1>, Shape<R2, R2, R2, C2, 1>, MINB1, MINB2>;
 
 // Supported sizes.  f32: 32x32 register stages (1024-point tiles); f64: 16x16 (256-point tiles).
 template <typename T> const TwoPassOps<T>* lookup(size_t n);
@@ -134,7 +146,13 @@ template <> inline const TwoPassOps<float>* lookup<float>(size_t n) {
       if (env && atoi(env) == 16) return TwoPass<float, 32, 32, 16, 16, 0, 1, 1>::ops();
       return TwoPass<float, 32, 32, 8, 8, 8, 2, 2>::ops();
     }
+    case (size_t)1 << 12: return TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>::ops();
+    case (size_t)1 << 13: return TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>::ops();
+    case (size_t)1 << 14: return TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>::ops();
+    case (size_t)1 << 15: return TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<16, 16, 16, 16, 1>, 4, 2>::ops();
     case (size_t)1 << 16: return TwoPass<float, 16, 16, 16, 16, 0, 2, 2>::ops();
+    case (size_t)1 << 17: return TwoPassG<float, Shape<16, 16, 16, 16, 0>, Shape<16, 32, 32, 8, 1>, 2, 2>::ops();
+    case (size_t)1 << 19: return TwoPassG<float, Shape<16, 32, 32, 8, 8>, Shape<32, 32, 32, 8, 1>, 2, 2>::ops();
     case (size_t)1 << 18: return TwoPass<float, 16, 32, 16, 8, 0, 2, 2>::ops();
     default: return nullptr;
   }
@@ -143,6 +161,8 @@ template <> inline const TwoPassOps<double>* lookup<double>(size_t n) {
   switch (n) {
     case (size_t)1 << 16: return TwoPass<double, 16, 16, 8, 8, 4, 2, 2>::ops();
     case (size_t)1 << 12: return TwoPass<double, 8, 8, 16, 16, 0, 4, 4>::ops();
+    case (size_t)1 << 13: return TwoPassG<double, Shape<8, 8, 8, 16, 0>, Shape<8, 16, 16, 8, 1>, 4, 2>::ops();
+    case (size_t)1 << 15: return TwoPassG<double, Shape<8, 16, 16, 8, 4>, Shape<16, 16, 16, 8, 1>, 2, 2>::ops();
     case (size_t)1 << 14: return TwoPass<double, 8, 16, 16, 8, 0, 4, 2>::ops();
     default: return nullptr;
   }

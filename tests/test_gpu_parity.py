@@ -96,7 +96,9 @@ def test_all_codes_vs_oracle(real, code):
 
 
 @pytest.mark.parametrize("real,n", [("f32", 1 << 20), ("f64", 1 << 16), ("f32", 1 << 16), ("f64", 1 << 20),
-                                    ("f32", 1 << 18), ("f32", 3 << 18), ("f64", 1 << 14), ("f32", 1 << 22)])
+                                    ("f32", 1 << 18), ("f32", 3 << 18), ("f64", 1 << 14), ("f32", 1 << 22),
+                                    ("f32", 1 << 13), ("f32", 1 << 15), ("f32", 1 << 17), ("f32", 1 << 19),
+                                    ("f64", 1 << 13), ("f64", 1 << 15)])
 def test_large_sizes_vs_oracle(real, n):
     x = O.fill_input(3, n, NP[real], first_transform=11)
     p = create(real, n)
@@ -177,7 +179,7 @@ def test_device_input_generator_matches_oracle(real):
 
 
 @pytest.mark.parametrize("real", ["f32", "f64"])
-@pytest.mark.parametrize("n", [64, 1024, 4096, 1 << 14, 1 << 16, 1 << 20])
+@pytest.mark.parametrize("n", [64, 128, 512, 1024, 4096, 1 << 13, 1 << 14, 1 << 15, 1 << 16, 1 << 17, 1 << 19, 1 << 20])
 def test_fused_paths_agree_with_general_path(real, n):
     # the one-kernel-per-stage path is an independent implementation of the same transform
     x = O.fill_input(3, n, NP[real], first_transform=1)

@@ -305,6 +305,14 @@ int main() {
   bad += check<float, TwoPass<float, 32, 32, 16, 16, 0, 1, 1>>("f32 2^20 (C=16)", 2e-6);
   bad += check<float, TwoPass<float, 16, 16, 16, 16, 0, 2, 2>>("f32 2^16", 2e-6);
   bad += check<float, TwoPass<float, 16, 32, 16, 8, 0, 2, 2>>("f32 2^18", 2e-6);
+  bad += check<float, TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>>("f32 2^12", 2e-6);
+  bad += check<float, TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>>("f32 2^13", 2e-6);
+  bad += check<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>>("f32 2^14", 2e-6);
+  bad += check<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<16, 16, 16, 16, 1>, 4, 2>>("f32 2^15", 2e-6);
+  bad += check<float, TwoPassG<float, Shape<16, 16, 16, 16, 0>, Shape<16, 32, 32, 8, 1>, 2, 2>>("f32 2^17", 2e-6);
+  bad += check<float, TwoPassG<float, Shape<16, 32, 32, 8, 8>, Shape<32, 32, 32, 8, 1>, 2, 2>>("f32 2^19", 2e-6);
+  bad += check<double, TwoPassG<double, Shape<8, 8, 8, 16, 0>, Shape<8, 16, 16, 8, 1>, 4, 2>>("f64 2^13", 5e-15);
+  bad += check<double, TwoPassG<double, Shape<8, 16, 16, 8, 4>, Shape<16, 16, 16, 8, 1>, 2, 2>>("f64 2^15", 5e-15);
   bad += check<double, TwoPass<double, 16, 16, 8, 8, 4, 2, 2>>("f64 2^16", 5e-15);
   bad += check<double, TwoPass<double, 8, 8, 16, 16, 0, 4, 4>>("f64 2^12", 5e-15);
   bad += check<double, TwoPass<double, 8, 16, 16, 8, 0, 4, 2>>("f64 2^14", 5e-15);
