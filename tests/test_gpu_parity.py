@@ -110,6 +110,26 @@ def test_large_sizes_vs_oracle(real, n):
         assert e < TOL[real], (n, code, e)
 
 
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_random_sizes_all_paths(real):
+    """60 pseudo-random sizes up to 40000 (primes, prime powers, {2,3}-smooth, odd composites): every path
+    (on-chip, two-pass tiles, general stages, fused and unfused Bluestein) against the oracle."""
+    rng = np.random.default_rng(2026)
+    sizes = set(int(v) for v in rng.integers(2, 6000, 30)) | set(int(v) for v in rng.integers(6000, 40000, 12))
+    sizes |= {997, 1021, 1031, 2047, 2048, 2049, 3 * 1024, 5 * 1024, 9 * 512, 2 * 3 ** 7, 7 ** 4, 4093, 8191, 10007, 3 ** 9}
+    seen = {}
+    for n in sorted(sizes):
+        x = (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))).astype(NP[real])
+        p = create(real, n)
+        seen[p.info()["path_name"]] = seen.get(p.info()["path_name"], 0) + 1
+        for code in (T.Fft, T.SqrtScaledIfft):
+            e = rel_err(gpu_transform(p, x, code), O.transform(x, int(code)))
+            assert e < TOL[real], (n, code, p.info()["path_name"], e)
+        p.close()
+    print(real, "paths exercised:", seen)
+    assert {"global_stages", "bluestein", "bluestein_fused"} <= set(seen)
+
+
 def test_config1_single_1024_via_reference_abi():
     # BASELINE.json configs[0]: one 1024-point c-f32 forward FFT through fourier_create_float +
     # fourier_transform_float with host buffers
