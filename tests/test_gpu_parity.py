@@ -123,8 +123,17 @@ def test_random_sizes_all_paths(real):
         p = create(real, n)
         seen[p.info()["path_name"]] = seen.get(p.info()["path_name"], 0) + 1
         for code in (T.Fft, T.SqrtScaledIfft):
-            e = rel_err(gpu_transform(p, x, code), O.transform(x, int(code)))
-            assert e < TOL[real], (n, code, p.info()["path_name"], e)
+            got, want = gpu_transform(p, x, code), O.transform(x, int(code))
+            e = rel_err(got, want)
+            if e >= TOL[real]:
+                # The reference forms the Bluestein chirp angle pi*i^2/N in f64 WITHOUT reducing i^2 mod 2N
+                # (bluesteins.rs:31,33,57), so for N in the thousands its own f64 result is only good to
+                # ~1e-12; the GPU plan reduces the index exactly.  Accept a discrepancy only if it is the
+                # oracle's distance from the f64 truth and the GPU result is an order of magnitude closer.
+                truth = truth_f64(x, int(code))
+                assert p.info()["path_name"].startswith("bluestein"), (n, code, e)
+                assert rel_err(got, truth) < TOL[real] / 10 and rel_err(want, truth) > e / 2, (n, code, e)
+            assert e < 3 * TOL[real], (n, code, p.info()["path_name"], e)
         p.close()
     print(real, "paths exercised:", seen)
     assert {"global_stages", "bluestein", "bluestein_fused"} <= set(seen)
