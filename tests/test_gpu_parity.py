@@ -132,8 +132,10 @@ def test_random_sizes_all_paths(real):
                 # oracle's distance from the f64 truth and the GPU result is an order of magnitude closer.
                 truth = truth_f64(x, int(code))
                 assert p.info()["path_name"].startswith("bluestein"), (n, code, e)
+                # (measured on B200, f64: N=2804 gpu-vs-truth 7e-16, oracle-vs-truth 1.1e-12; N=30011: 1e-15 vs 1.3e-11)
                 assert rel_err(got, truth) < TOL[real] / 10 and rel_err(want, truth) > e / 2, (n, code, e)
-            assert e < 3 * TOL[real], (n, code, p.info()["path_name"], e)
+                continue
+            assert e < TOL[real], (n, code, p.info()["path_name"], e)
         p.close()
     print(real, "paths exercised:", seen)
     assert {"global_stages", "bluestein", "bluestein_fused"} <= set(seen)
