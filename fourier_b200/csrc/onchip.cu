@@ -4,6 +4,7 @@
 // Bluesteins::transform_in_place / apply (bluesteins.rs:193-259).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "onchip_kernels.cuh"
 #include "plan.h"
@@ -35,13 +36,13 @@ template <typename T> struct OnChipOps {
                            cudaStream_t);
 };
 
-template <typename T, int RA, int RB, int E, int WARPS, int MINB, int BWARPS>
+template <typename T, int RA, int RB, int E, int WARPS, int MINB, int BWARPS, bool LOCAL_STASH = false>
 struct OnChipImpl {
   template <bool FWD> using Cfg = OnChipCfg<T, RA, RB, E, WARPS, FWD>;
   using BCfg = OnChipCfg<T, RA, RB, E, BWARPS, true>;
   static constexpr size_t smem_fft = Cfg<true>::EX_BYTES + Cfg<true>::TWA_BYTES;
   static constexpr size_t smem_blue =
-      BCfg::EX_BYTES + BCfg::TWA_BYTES + sizeof(cpx<T>) * (4 * (size_t)BCfg::L + (size_t)E * BCfg::THREADS);
+      BCfg::EX_BYTES + BCfg::TWA_BYTES + sizeof(cpx<T>) * (4 * (size_t)BCfg::L + (LOCAL_STASH ? 0 : (size_t)E * BCfg::THREADS));
   static constexpr bool kHasBluestein = (RA == RB) && (E == RA);
 
   static cudaError_t prepare() {
@@ -51,7 +52,7 @@ struct OnChipImpl {
     if ((e = cudaFuncSetAttribute(onchip::onchip_fft_kernel<Cfg<false>, MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft))) return e;
     if constexpr (kHasBluestein) {
-      if ((e = cudaFuncSetAttribute(onchip::bluestein_fused_kernel<BCfg, 1>,
+      if ((e = cudaFuncSetAttribute(onchip::bluestein_fused_kernel<BCfg, 1, LOCAL_STASH>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blue))) return e;
     }
     return cudaSuccess;
@@ -77,7 +78,7 @@ struct OnChipImpl {
       const unsigned grid = (unsigned)std::min<size_t>(groups, (size_t)sms * 2);
       typename onchip::BluesteinBody<BCfg>::Args a = {in, out, (const TwPair<T>*)twa, chirp, wm, wce, wco,
                                                       (long)n, (long)batch, scale};
-      onchip::bluestein_fused_kernel<BCfg, 1><<<grid, BCfg::THREADS, smem_blue, s>>>(a);
+      onchip::bluestein_fused_kernel<BCfg, 1, LOCAL_STASH><<<grid, BCfg::THREADS, smem_blue, s>>>(a);
       return cudaGetLastError();
     } else {
       return cudaErrorNotSupported;
@@ -97,7 +98,13 @@ template <> const OnChipOps<float>* onchip_lookup<float>(size_t l) {
     case 128: return OnChipImpl<float, 8, 16, 16, 8, 4, 8>::ops();
     case 256: return OnChipImpl<float, 16, 16, 16, 8, 3, 8>::ops();
     case 512: return OnChipImpl<float, 16, 32, 32, 8, 2, 8>::ops();
-    case 1024: return OnChipImpl<float, 32, 32, 32, 8, 2, 11>::ops();
+    case 1024:
+      // The fused Bluestein kernel parks the even half in thread-local memory (16 warps per SM, measured
+      // 1.16e11 samples/s at N=1009); FOURIER_B200_BLUESTEIN_LOCAL=0 selects the shared-memory stash
+      // (11 warps per SM, 1.01e11).
+      if (const char* e = std::getenv("FOURIER_B200_BLUESTEIN_LOCAL"); e && atoi(e) == 0)
+        return OnChipImpl<float, 32, 32, 32, 8, 2, 11>::ops();
+      return OnChipImpl<float, 32, 32, 32, 8, 2, 16, true>::ops();
     default: return nullptr;
   }
 }

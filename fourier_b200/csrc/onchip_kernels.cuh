@@ -183,6 +183,23 @@ template <class Cfg> struct BluesteinBody {
   static FB_HD void stash_even(const Tile& f, int t, V* stash) {
     static_for<0, E>([&](auto I) FB_LAMBDA { constexpr int i = decltype(I)::value; stash[i * Cfg::THREADS + t] = f.v[i]; });
   }
+  static FB_HD void combine_store_local(const V (&keep)[E], const Tile& f, const Args& a, long b, int t, const V* chirp,
+                                        const V* wm) {
+    const int u = Tile::template u_of<true>(t);
+    V* p = a.out + b * a.n;
+    static_for<0, Tile::NB>([&](auto Cc) FB_LAMBDA {
+      constexpr int c = decltype(Cc)::value;
+      static_for<0, RB>([&](auto Rr) FB_LAMBDA {
+        constexpr int r = decltype(Rr)::value;
+        const int n = pos_out(u, c, r);
+        if (n < a.n) {
+          constexpr int idx = c * RB + bitrev(r, ilog2(RB));
+          const V o = cmul(f.v[idx], wm[n]);
+          p[n] = cscale(cmul_conja(cadd(keep[idx], o), chirp[n]), a.scale);
+        }
+      });
+    });
+  }
   static FB_HD void combine_store(const V* stash, const Tile& f, const Args& a, long b, int t, const V* chirp,
                                   const V* wm) {
     const int u = Tile::template u_of<true>(t);
@@ -203,7 +220,7 @@ template <class Cfg> struct BluesteinBody {
   }
 };
 
-template <class Cfg, int MINB>
+template <class Cfg, int MINB, bool LOCAL_STASH = false>
 __global__ void __launch_bounds__(Cfg::THREADS, MINB)
 bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
   using Body = BluesteinBody<Cfg>;
@@ -215,7 +232,10 @@ bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(smem_raw + Cfg::EX_BYTES);
   V* tabs = reinterpret_cast<V*>(smem_raw + Cfg::EX_BYTES + Cfg::TWA_BYTES);
   V* chirp = tabs; V* wm = tabs + L; V* wce = tabs + 2 * L; V* wco = tabs + 3 * L;
-  V* stash = tabs + 4 * L;   // [E][THREADS]
+  V* stash_smem = tabs + 4 * L;   // [E][THREADS] (unused with LOCAL_STASH)
+  // LOCAL_STASH: E' of the even half waits in a per-thread array instead (registers if they fit, else
+  // thread-local memory behind L1/L2): frees 8 KB of shared memory per warp -> more resident warps.
+  V keep[LOCAL_STASH ? Cfg::Tile::E : 1];
   for (int i = threadIdx.x; i < (Cfg::Tile::RA / 2) * Cfg::Tile::RB; i += Cfg::THREADS) twa[i] = a.twa[i];
   for (int i = threadIdx.x; i < L; i += Cfg::THREADS) {
     chirp[i] = a.chirp[i]; wm[i] = a.wm[i]; wce[i] = a.wce[i]; wco[i] = a.wco[i];
@@ -236,7 +256,11 @@ bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
     Body::second_fft_start(f, t, exch, twa);
     __syncwarp();
     Body::second_fft_finish(f, t, exch);
-    Body::stash_even(f, t, stash);
+    if constexpr (LOCAL_STASH) {
+      static_for<0, Cfg::Tile::E>([&](auto I) FB_LAMBDA { constexpr int i = decltype(I)::value; keep[i] = f.v[i]; });
+    } else {
+      Body::stash_even(f, t, stash_smem);
+    }
     __syncwarp();
     // odd half
     Body::template load_half<true>(f, a, b, t, exch, twa, chirp, wm);
@@ -246,7 +270,10 @@ bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
     Body::second_fft_start(f, t, exch, twa);
     __syncwarp();
     Body::second_fft_finish(f, t, exch);
-    if (b_real < a.batch) Body::combine_store(stash, f, a, b, t, chirp, wm);
+    if (b_real < a.batch) {
+      if constexpr (LOCAL_STASH) Body::combine_store_local(keep, f, a, b, t, chirp, wm);
+      else Body::combine_store(stash_smem, f, a, b, t, chirp, wm);
+    }
     __syncwarp();
   }
 }
