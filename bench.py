@@ -33,6 +33,8 @@ WORKLOADS = {
     "c2": (1 << 20, 4096, "f32", "batched N=2^20 c-f32 forward, batch 4096 per GPU (BASELINE configs[1])"),
     "c3": (1 << 16, 65536, "f64", "batched N=2^16 c-f64 forward, batch 65536 (BASELINE configs[2])"),
     "c4": (1009, 1 << 20, "f32", "prime N=1009 Bluestein c-f32 forward, batch 2^20 (BASELINE configs[3])"),
+    "c5": (1 << 30, 1, "f32", "single distributed N=2^30 c-f32 over all ranks, six-step with NCCL all-to-all "
+                              "transposes (BASELINE configs[4])"),
 }
 BYTES_PER_SAMPLE = {"f32": 16, "f64": 32}  # algorithmic: read once + write once
 
@@ -160,6 +162,62 @@ def run_reference(args, n, batch, real, rank, world):
     }))
 
 
+def run_distributed(args, rank, local_rank, world, barrier):
+    """BASELINE configs[4]: ONE transform of N = 2^30 (or 2^--log2n) samples block-distributed over the ranks."""
+    import torch
+    import torch.distributed as dist
+    import fourier_b200 as fb
+    from fourier_b200.distributed import CudaBackend, DistributedFft
+    k = args.log2n
+    n1, n2 = 1 << (k // 2), 1 << (k - k // 2)
+    n = n1 * n2
+    blk = n // world
+    x = torch.empty(blk, dtype=torch.complex64, device="cuda")
+    s = torch.empty_like(x)
+    fb.fill_input(x.view(1, blk), first_transform=rank)
+    plan = DistributedFft(n1, n2, rank, world, CudaBackend("f32"))
+    cur, oth = x, s
+    for _ in range(args.warmup):
+        out = plan.transform(cur, oth)
+        cur, oth = (out, oth if out is cur else cur)
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        start.record()
+        for _ in range(args.steps):
+            out = plan.transform(cur, oth)
+            cur, oth = (out, oth if out is cur else cur)
+        stop.record()
+        barrier()
+    ms = torch.tensor([start.elapsed_time(stop)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    ms_per_step = float(ms.item()) / args.steps
+    wire = plan.wire_bytes_per_exchange(8) * 3
+    peak, peak_src = measured_peak()
+    local_bytes = blk * 8 * 2 * (2 + 6 + 1)     # per GPU: 2 FFT batches, 3 x (transpose + swap), twiddle: read + write each
+    achieved = local_bytes / (ms_per_step * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": "distributed 1D FFT complex-samples/sec (one N=2^%d transform)" % k, "value": n / (ms_per_step * 1e-3),
+        "unit": "complex samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS["c5"][3], "N": n, "n1": n1, "n2": n2,
+                   "parallelism": f"block-distributed over {world} ranks, 3 all-to-all transposes",
+                   "note": "successive steps transform the previous result (ping-pong buffers)"},
+        "nvlink": {"bytes_sent_per_gpu_per_step": wire,
+                   "achieved_gbs_per_gpu_per_direction_if_exchanges_were_the_whole_step": wire / (ms_per_step * 1e-3) / 1e9,
+                   "reference_gbs": 770, "reference": "measured peer copy per direction (B200_PROFILING.md)"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "note": "local passes only: 9 read+write sweeps of the rank's block per step (unfused)"},
+        "gpu_launches": None, "clocks": clocks.summary(),
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +230,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--verify", type=int, default=4, help="transforms checked against the oracle")
+    ap.add_argument("--log2n", type=int, default=30, help="c5 only: log2 of the distributed transform length")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -202,6 +261,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.workload == "c5":
+        run_distributed(args, rank, local_rank, world, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cdt = torch.complex64 if real == "f32" else torch.complex128
     plan = fb.create_fft_f32(n) if real == "f32" else fb.create_fft_f64(n)

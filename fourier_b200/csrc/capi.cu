@@ -197,6 +197,27 @@ int fourier_b200_fill_input_double(void* dev_out, unsigned long long first, size
   return (int)fb200::launch_fill_input<double>((double*)dev_out, first, count, seed, (cudaStream_t)stream);
 }
 
+int fourier_b200_transpose_float(const void* in, void* out, size_t batch, size_t rows, size_t cols, void* stream) {
+  return (int)fb200::launch_transpose<float>((const float2*)in, (float2*)out, batch, rows, cols, (cudaStream_t)stream);
+}
+int fourier_b200_transpose_double(const void* in, void* out, size_t batch, size_t rows, size_t cols, void* stream) {
+  return (int)fb200::launch_transpose<double>((const double2*)in, (double2*)out, batch, rows, cols, (cudaStream_t)stream);
+}
+int fourier_b200_swap_leading_float(const void* in, void* out, size_t a, size_t b, size_t inner, void* stream) {
+  return (int)fb200::launch_swap_leading<float>((const float2*)in, (float2*)out, a, b, inner, (cudaStream_t)stream);
+}
+int fourier_b200_swap_leading_double(const void* in, void* out, size_t a, size_t b, size_t inner, void* stream) {
+  return (int)fb200::launch_swap_leading<double>((const double2*)in, (double2*)out, a, b, inner, (cudaStream_t)stream);
+}
+int fourier_b200_twiddle_rows_float(void* data, size_t rows, size_t cols, unsigned long long row0,
+                                    unsigned long long n_total, int forward, void* stream) {
+  return (int)fb200::launch_twiddle_rows<float>((float2*)data, rows, cols, row0, n_total, forward != 0, (cudaStream_t)stream);
+}
+int fourier_b200_twiddle_rows_double(void* data, size_t rows, size_t cols, unsigned long long row0,
+                                     unsigned long long n_total, int forward, void* stream) {
+  return (int)fb200::launch_twiddle_rows<double>((double2*)data, rows, cols, row0, n_total, forward != 0, (cudaStream_t)stream);
+}
+
 const char* fourier_b200_last_error(void) { return fb200::last_error(); }
 const char* fourier_b200_version(void) { return "fourier-b200 0.1.0 (sm_100a)"; }
 

@@ -165,6 +165,15 @@ template <typename T>
 cudaError_t launch_fill_input(T* out, unsigned long long first_scalar, size_t count,
                               unsigned long long seed, cudaStream_t s);
 
+// synth.cu: helpers of the distributed six-step transform
+template <typename T>
+cudaError_t launch_transpose(const cpx<T>* in, cpx<T>* out, size_t batch, size_t rows, size_t cols, cudaStream_t s);
+template <typename T>
+cudaError_t launch_swap_leading(const cpx<T>* in, cpx<T>* out, size_t a, size_t b, size_t inner, cudaStream_t s);
+template <typename T>
+cudaError_t launch_twiddle_rows(cpx<T>* data, size_t rows, size_t cols, unsigned long long row0,
+                                unsigned long long n_total, bool forward, cudaStream_t s);
+
 // host math helpers (plan_math.cpp part of plan.cu)
 void host_twiddle(size_t k, size_t n, double* re, double* im);            // exp(-2*pi*i*k/n), long-double accurate
 void host_fft_pow2(std::vector<double>& re, std::vector<double>& im, bool inverse);  // unscaled, in place

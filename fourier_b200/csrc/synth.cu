@@ -28,7 +28,90 @@ fill_kernel(T* __restrict__ out, unsigned long long first, size_t count, unsigne
     out[g] = unit(hash64(seed, first + g), T());
 }
 
+
+// ---- helpers of the distributed six-step transform (BASELINE config 5) ------------------------------------------
+// Batched 2-D transpose out[b][c][r] = in[b][r][c] through a padded 32x32 shared-memory tile: both the read
+// and the write are contiguous along the fastest index.
+template <typename V>
+__global__ void __launch_bounds__(256)
+transpose_kernel(const V* __restrict__ in, V* __restrict__ out, size_t rows, size_t cols) {
+  __shared__ V tile[32][33];
+  const size_t b = blockIdx.z;
+  const V* src = in + b * rows * cols;
+  V* dst = out + b * rows * cols;
+  const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8)
+    if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = src[(r0 + i) * cols + c0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) dst[(c0 + i) * rows + r0 + tx] = tile[tx][i];
+}
+
+// out[b][a][i] = in[a][b][i]: swaps the two leading axes of a 3-D array whose innermost runs (i < inner)
+// stay contiguous -- the unpack step after an all-to-all (received [src rank][my row][their rows]).
+template <typename V>
+__global__ void __launch_bounds__(256)
+swap_leading_kernel(const V* __restrict__ in, V* __restrict__ out, size_t a, size_t b, size_t inner) {
+  const size_t total = a * b * inner;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = g % inner, ab = g / inner, aa = ab % a, bb = ab / a;   // g enumerates out[bb][aa][i]
+    out[g] = in[(aa * b + bb) * inner + i];
+  }
+}
+
+// data[r][c] *= w_N^{(row0 + r) * c} (conjugated for the inverse direction).  The angle index is reduced
+// mod N in 64-bit integers and the twiddle evaluated in double (sincospi), so it is exact to T's precision
+// even for N = 2^30, where a float cannot hold the index.
+template <typename T, bool FWD>
+__global__ void __launch_bounds__(256)
+twiddle_rows_kernel(cpx<T>* __restrict__ data, size_t rows, size_t cols, unsigned long long row0,
+                    unsigned long long n_total) {
+  const size_t total = rows * cols;
+  for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < total; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = g / cols, c = g - r * cols;
+    const unsigned long long m = ((row0 + r) * (unsigned long long)c) % n_total;
+    double sn, cs;
+    sincospi(2.0 * (double)m / (double)n_total, &sn, &cs);
+    const cpx<T> w = mk<T>((T)cs, (T)(-sn));
+    data[g] = ctw<FWD>(data[g], w);
+  }
+}
+
 }  // namespace
+
+template <typename T>
+cudaError_t launch_transpose(const cpx<T>* in, cpx<T>* out, size_t batch, size_t rows, size_t cols, cudaStream_t s) {
+  if (batch == 0 || rows == 0 || cols == 0) return cudaSuccess;
+  if (batch > 65535 || (rows + 31) / 32 > 65535) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch);
+  transpose_kernel<cpx<T>><<<grid, 256, 0, s>>>(in, out, rows, cols);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t launch_swap_leading(const cpx<T>* in, cpx<T>* out, size_t a, size_t b, size_t inner, cudaStream_t s) {
+  size_t blocks = (a * b * inner + 255) / 256;
+  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  if (blocks == 0) return cudaSuccess;
+  swap_leading_kernel<cpx<T>><<<(unsigned)blocks, 256, 0, s>>>(in, out, a, b, inner);
+  return cudaGetLastError();
+}
+template cudaError_t launch_swap_leading<float>(const cpx<float>*, cpx<float>*, size_t, size_t, size_t, cudaStream_t);
+template cudaError_t launch_swap_leading<double>(const cpx<double>*, cpx<double>*, size_t, size_t, size_t, cudaStream_t);
+template <typename T>
+cudaError_t launch_twiddle_rows(cpx<T>* data, size_t rows, size_t cols, unsigned long long row0,
+                                unsigned long long n_total, bool forward, cudaStream_t s) {
+  size_t blocks = (rows * cols + 255) / 256;
+  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  if (blocks == 0) return cudaSuccess;
+  if (forward) twiddle_rows_kernel<T, true><<<(unsigned)blocks, 256, 0, s>>>(data, rows, cols, row0, n_total);
+  else twiddle_rows_kernel<T, false><<<(unsigned)blocks, 256, 0, s>>>(data, rows, cols, row0, n_total);
+  return cudaGetLastError();
+}
+template cudaError_t launch_transpose<float>(const cpx<float>*, cpx<float>*, size_t, size_t, size_t, cudaStream_t);
+template cudaError_t launch_transpose<double>(const cpx<double>*, cpx<double>*, size_t, size_t, size_t, cudaStream_t);
+template cudaError_t launch_twiddle_rows<float>(cpx<float>*, size_t, size_t, unsigned long long, unsigned long long, bool, cudaStream_t);
+template cudaError_t launch_twiddle_rows<double>(cpx<double>*, size_t, size_t, unsigned long long, unsigned long long, bool, cudaStream_t);
 
 template <typename T>
 cudaError_t launch_fill_input(T* out, unsigned long long first_scalar, size_t count,

@@ -77,6 +77,24 @@ int fourier_b200_fill_input_float(void *dev_out, unsigned long long first_scalar
 int fourier_b200_fill_input_double(void *dev_out, unsigned long long first_scalar, size_t count,
                                    unsigned long long seed, void *cuda_stream);
 
+/* Building blocks of the distributed six-step transform (one huge N = N1*N2 over several GPUs with
+ * all-to-all transposes between local batched FFTs; fourier_b200/distributed.py drives them):
+ * batched 2-D transpose out[b][c][r] = in[b][r][c], and data[r][c] *= w_N^{(row0+r)*c} (conj if !forward)
+ * with the index reduced exactly mod N.  Device pointers, enqueued on cuda_stream. */
+int fourier_b200_transpose_float(const void *in_dev, void *out_dev, size_t batch, size_t rows, size_t cols,
+                                 void *cuda_stream);
+int fourier_b200_transpose_double(const void *in_dev, void *out_dev, size_t batch, size_t rows, size_t cols,
+                                  void *cuda_stream);
+/* out[b][a][i] = in[a][b][i] (i < inner contiguous): unpack step after an all-to-all */
+int fourier_b200_swap_leading_float(const void *in_dev, void *out_dev, size_t a, size_t b, size_t inner,
+                                    void *cuda_stream);
+int fourier_b200_swap_leading_double(const void *in_dev, void *out_dev, size_t a, size_t b, size_t inner,
+                                     void *cuda_stream);
+int fourier_b200_twiddle_rows_float(void *data_dev, size_t rows, size_t cols, unsigned long long row0,
+                                    unsigned long long n_total, int forward, void *cuda_stream);
+int fourier_b200_twiddle_rows_double(void *data_dev, size_t rows, size_t cols, unsigned long long row0,
+                                     unsigned long long n_total, int forward, void *cuda_stream);
+
 const char *fourier_b200_last_error(void);
 const char *fourier_b200_version(void);
 

@@ -1,0 +1,69 @@
+"""Host logic of the distributed six-step transform (fourier_b200/distributed.py) on CPU: world-size-2 and
+-4 gloo runs with numpy standing in for the local GPU kernels, against numpy's FFT of the whole signal.
+This checks the exchange pattern, block distribution and inter-step twiddle indices; the CUDA backend
+itself is checked on the GPU box (tests/test_gpu_distributed.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, n1, n2, forward, q):
+    sys.path.insert(0, ROOT)
+    from fourier_b200.distributed import DistributedFft, NumpyBackend
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = n1 * n2
+    rng = np.random.default_rng(7)
+    full = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex128)
+    blk = n // world
+    x = torch.from_numpy(full[rank * blk:(rank + 1) * blk].copy())
+    scratch = torch.empty_like(x)
+    plan = DistributedFft(n1, n2, rank, world, NumpyBackend())
+    out = plan.transform(x, scratch, forward=forward)
+    want = np.fft.fft(full) if forward else np.fft.ifft(full) * n
+    err = np.abs(out.numpy() - want[rank * blk:(rank + 1) * blk]).max() / np.abs(want).max()
+    q.put((rank, float(err)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n1,n2,forward", [(2, 8, 16, True), (2, 32, 8, False), (4, 16, 16, True)])
+def test_six_step_exchange_logic(world, n1, n2, forward):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n1, n2, forward, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    errs = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert len(errs) == world and max(errs.values()) < 1e-12, errs
+
+
+def test_single_rank_degenerates_to_local_transposes():
+    sys.path.insert(0, ROOT)
+    from fourier_b200.distributed import DistributedFft, NumpyBackend
+    n1, n2 = 8, 32
+    rng = np.random.default_rng(3)
+    full = (rng.standard_normal(n1 * n2) + 1j * rng.standard_normal(n1 * n2)).astype(np.complex128)
+    x = torch.from_numpy(full.copy())
+    out = DistributedFft(n1, n2, 0, 1, NumpyBackend()).transform(x, torch.empty_like(x))
+    assert np.abs(out.numpy() - np.fft.fft(full)).max() < 1e-11
