@@ -161,8 +161,8 @@ template <> inline const TwoPassOps<float>* lookup<float>(size_t n) {
 template <> inline const TwoPassOps<double>* lookup<double>(size_t n) {
   switch (n) {
     case (size_t)1 << 16: return TwoPass<double, 16, 16, 8, 8, 4, 2, 2>::ops();
-    case (size_t)1 << 9: return TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 1>, 4, 4>::ops();
-    case (size_t)1 << 10: return TwoPassG<double, Shape<4, 8, 8, 16, 0>, Shape<4, 8, 8, 16, 1>, 4, 4>::ops();
+    case (size_t)1 << 9: return TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>::ops();
+    case (size_t)1 << 10: return TwoPassG<double, Shape<4, 8, 8, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>::ops();
     case (size_t)1 << 11: return TwoPassG<double, Shape<4, 8, 8, 16, 0>, Shape<8, 8, 8, 16, 1>, 4, 4>::ops();
     case (size_t)1 << 12: return TwoPass<double, 8, 8, 16, 16, 0, 4, 4>::ops();
     case (size_t)1 << 13: return TwoPassG<double, Shape<8, 8, 8, 16, 0>, Shape<8, 16, 16, 8, 1>, 4, 2>::ops();
