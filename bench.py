@@ -172,10 +172,9 @@ def run_distributed(args, rank, local_rank, world, barrier):
     n1, n2 = 1 << (k // 2), 1 << (k - k // 2)
     n = n1 * n2
     blk = n // world
-    x = torch.empty(blk, dtype=torch.complex64, device="cuda")
-    s = torch.empty_like(x)
+    plan = DistributedFft(n1, n2, rank, world, CudaBackend("f32"), exchange=args.exchange)
+    x, s = plan.buffers()
     fb.fill_input(x.view(1, blk), first_transform=rank)
-    plan = DistributedFft(n1, n2, rank, world, CudaBackend("f32"))
     cur, oth = x, s
     for _ in range(args.warmup):
         out = plan.transform(cur, oth)
@@ -198,7 +197,10 @@ def run_distributed(args, rank, local_rank, world, barrier):
     ms_per_step = float(ms.item()) / args.steps
     wire = plan.wire_bytes_per_exchange(8) * 3
     peak, peak_src = measured_peak()
-    local_bytes = blk * 8 * 2 * (2 + 6 + 1)     # per GPU: 2 FFT batches, 3 x (transpose + swap), twiddle: read + write each
+    # per GPU and step, read + write each: 2 FFT batches and 3 exchanges (one sweep each over NVLink peer memory;
+    # pack + all_to_all + unpack = 3 sweeps with NCCL)
+    sweeps = 2 + (3 if plan.exchange == "peer" else 9)
+    local_bytes = blk * 8 * 2 * sweeps
     achieved = local_bytes / (ms_per_step * 1e-3) / 1e9
     print(json.dumps({
         "metric": "distributed 1D FFT complex-samples/sec (one N=2^%d transform)" % k, "value": n / (ms_per_step * 1e-3),
@@ -206,14 +208,18 @@ def run_distributed(args, rank, local_rank, world, barrier):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS["c5"][3], "N": n, "n1": n1, "n2": n2,
-                   "parallelism": f"block-distributed over {world} ranks, 3 all-to-all transposes",
+                   "parallelism": (f"block-distributed over {world} ranks, 3 exchanges, each ONE transposing kernel storing "
+                                   "into the peers' buffers over NVLink (CUDA IPC) + a stream-ordered barrier"
+                                   if plan.exchange == "peer" else
+                                   f"block-distributed over {world} ranks, 3 NCCL all-to-all transposes, each "
+                                   f"pipelined in {plan.chunks} pieces"),
                    "note": "successive steps transform the previous result (ping-pong buffers)"},
         "nvlink": {"bytes_sent_per_gpu_per_step": wire,
                    "achieved_gbs_per_gpu_per_direction_if_exchanges_were_the_whole_step": wire / (ms_per_step * 1e-3) / 1e9,
                    "reference_gbs": 770, "reference": "measured peer copy per direction (B200_PROFILING.md)"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
-                     "note": "local passes only: 9 read+write sweeps of the rank's block per step (unfused)"},
+                     "note": f"local sweeps only: {sweeps} read+write sweeps of the rank's block per step"},
         "gpu_launches": None, "clocks": clocks.summary(),
     }))
 
@@ -231,6 +237,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--verify", type=int, default=4, help="transforms checked against the oracle")
     ap.add_argument("--log2n", type=int, default=30, help="c5 only: log2 of the distributed transform length")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="c5 only: exchanges as one kernel over NVLink peer memory, or pack + NCCL all_to_all + unpack")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

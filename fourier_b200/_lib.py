@@ -23,10 +23,11 @@ REFERENCE_SYMBOLS = [f"fourier_{op}_{t}" for t in ("float", "double")
                      for op in ("create", "destroy", "transform_in_place", "transform")]
 EXTENSION_SYMBOLS = (
     ["fourier_b200_set_device", "fourier_b200_get_device", "fourier_b200_device_count",
+     "fourier_b200_peer_alloc", "fourier_b200_peer_open", "fourier_b200_peer_close", "fourier_b200_peer_free",
      "fourier_b200_path_name", "fourier_b200_last_error", "fourier_b200_version"]
     + [f"fourier_b200_{op}_{t}" for t in ("float", "double")
        for op in ("transform_batch", "transform_batch_async", "plan_info", "create_general", "fill_input",
-                  "transpose", "swap_leading", "twiddle_rows")])
+                  "transpose", "pack", "exchange", "swap_leading", "twiddle_rows")])
 
 
 def load():
@@ -55,8 +56,16 @@ def load():
         getattr(L, f"fourier_b200_create_general_{t}").argtypes = [sz]
         getattr(L, f"fourier_b200_fill_input_{t}").argtypes = [vp, ctypes.c_ulonglong, sz, ctypes.c_ulonglong, vp]
         getattr(L, f"fourier_b200_transpose_{t}").argtypes = [vp, vp, sz, sz, sz, vp]
+        getattr(L, f"fourier_b200_pack_{t}").argtypes = [vp, vp, sz, sz, sz, sz, sz, sz, ci, ctypes.c_ulonglong,
+                                                       ctypes.c_ulonglong, ctypes.c_ulonglong, vp]
+        getattr(L, f"fourier_b200_exchange_{t}").argtypes = [vp, ctypes.POINTER(vp), ci, ci, sz, sz, sz, sz, sz, ci,
+                                                           ctypes.c_ulonglong, ctypes.c_ulonglong, vp]
         getattr(L, f"fourier_b200_swap_leading_{t}").argtypes = [vp, vp, sz, sz, sz, vp]
         getattr(L, f"fourier_b200_twiddle_rows_{t}").argtypes = [vp, sz, sz, ctypes.c_ulonglong, ctypes.c_ulonglong, ci, vp]
+    L.fourier_b200_peer_alloc.argtypes = [sz, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.fourier_b200_peer_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.fourier_b200_peer_close.argtypes = [vp]
+    L.fourier_b200_peer_free.argtypes = [vp]
     L.fourier_b200_set_device.argtypes = [ci]
     L.fourier_b200_path_name.restype = ctypes.c_char_p
     L.fourier_b200_path_name.argtypes = [ci]

@@ -203,6 +203,34 @@ int fourier_b200_transpose_float(const void* in, void* out, size_t batch, size_t
 int fourier_b200_transpose_double(const void* in, void* out, size_t batch, size_t rows, size_t cols, void* stream) {
   return (int)fb200::launch_transpose<double>((const double2*)in, (double2*)out, batch, rows, cols, (cudaStream_t)stream);
 }
+int fourier_b200_pack_float(const void* in, void* out, size_t batch, size_t rows, size_t cols, size_t ld, size_t ibs,
+                            size_t obs, int twiddle, unsigned long long row0, unsigned long long col0,
+                            unsigned long long n_total, void* stream) {
+  return (int)fb200::launch_pack<float>((const float2*)in, (float2*)out, batch, rows, cols, ld, ibs, obs, twiddle, row0,
+                                        col0, n_total, (cudaStream_t)stream);
+}
+int fourier_b200_pack_double(const void* in, void* out, size_t batch, size_t rows, size_t cols, size_t ld, size_t ibs,
+                             size_t obs, int twiddle, unsigned long long row0, unsigned long long col0,
+                             unsigned long long n_total, void* stream) {
+  return (int)fb200::launch_pack<double>((const double2*)in, (double2*)out, batch, rows, cols, ld, ibs, obs, twiddle, row0,
+                                         col0, n_total, (cudaStream_t)stream);
+}
+int fourier_b200_exchange_float(const void* in, void* const* outs, int nranks, int me, size_t rows, size_t cb, size_t ld,
+                                size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
+                                unsigned long long n_total, void* stream) {
+  return (int)fb200::launch_exchange<float>((const float2*)in, outs, nranks, me, rows, cb, ld, out_ld, out_off, twiddle,
+                                            row0, n_total, (cudaStream_t)stream);
+}
+int fourier_b200_exchange_double(const void* in, void* const* outs, int nranks, int me, size_t rows, size_t cb, size_t ld,
+                                 size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
+                                 unsigned long long n_total, void* stream) {
+  return (int)fb200::launch_exchange<double>((const double2*)in, outs, nranks, me, rows, cb, ld, out_ld, out_off, twiddle,
+                                             row0, n_total, (cudaStream_t)stream);
+}
+int fourier_b200_peer_alloc(size_t bytes, void** dev_ptr, void* handle64) { return (int)fb200::peer_alloc(bytes, dev_ptr, handle64); }
+int fourier_b200_peer_open(const void* handle64, void** dev_ptr) { return (int)fb200::peer_open(handle64, dev_ptr); }
+int fourier_b200_peer_close(void* dev_ptr) { return (int)fb200::peer_close(dev_ptr); }
+int fourier_b200_peer_free(void* dev_ptr) { return (int)fb200::peer_free(dev_ptr); }
 int fourier_b200_swap_leading_float(const void* in, void* out, size_t a, size_t b, size_t inner, void* stream) {
   return (int)fb200::launch_swap_leading<float>((const float2*)in, (float2*)out, a, b, inner, (cudaStream_t)stream);
 }

@@ -154,10 +154,17 @@ template <typename T> struct FusedArgs {
 };
 
 // Configuration: N = (R*R)^2, tiles of C FFTs, G consumer groups per CTA.
+// EXB_ > 0: EXB_ separate exchange buffers (group g uses g % EXB_, under a lock when shared); the staging
+//           buffer is released as soon as the samples are in registers.
+// EXB_ = 0: the exchange happens IN PLACE in the group's staging buffer, which is released after the
+//           gather; the refill then overlaps stage B and the stores.  Costs no prefetch distance that
+//           matters (a TMA round trip is shorter than stage B + stores) and frees a third of the shared
+//           memory, i.e. room for one more consumer group.
 template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1>
 struct FusedCfg {
   using T = T_;
-  static constexpr int R = R_, C = C_, G = G_, EXB = EXB_;   // EXB exchange buffers: group g uses g % EXB
+  static constexpr bool INPLACE = EXB_ == 0;
+  static constexpr int R = R_, C = C_, G = G_, EXB = INPLACE ? G_ : EXB_;
   static constexpr long L = (long)R * R, N1 = L, N2 = L, N = N1 * N2;
   template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
   using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
@@ -180,12 +187,16 @@ struct FusedCfg {
   static constexpr int EX_ELEMS = EX1 > EX2 ? EX1 : EX2;
   static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * EX_ELEMS + 127) / 128) * 128;
   static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (R / 2) * R;
-  // layout: staging[G] | exchange | twa | tile tables [G][2 bufs][base, step] | control
-  static constexpr size_t OFF_EX = (size_t)G * TILE_BYTES;
-  static constexpr size_t OFF_TWA = OFF_EX + (size_t)EXB * EX_BYTES;
+  // per-group buffer: the staged tile, and in the in-place mode also the (slightly larger) exchange
+  static constexpr size_t BUF_BYTES =
+      INPLACE ? (((EX_BYTES > TILE_BYTES ? EX_BYTES : TILE_BYTES) + 1023) / 1024) * 1024 : (size_t)TILE_BYTES;
+  static constexpr int TAB_BUFS = INPLACE ? 1 : 2;   // tile tables: own mbarrier pair (in place) or double buffer
+  // layout: staging[G] | exchange | twa | tile tables [G][TAB_BUFS][base, step] | control
+  static constexpr size_t OFF_EX = (size_t)G * BUF_BYTES;
+  static constexpr size_t OFF_TWA = OFF_EX + (INPLACE ? 0 : (size_t)EXB * EX_BYTES);
   static constexpr size_t OFF_TAB = OFF_TWA + TWA_BYTES;
-  static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 4 * TAB_BYTES;
-  static constexpr size_t SMEM_BYTES = OFF_CTL + 512 /* control block: G * sizeof(GroupCtl) + lock */;
+  static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * TAB_BUFS * 2 * TAB_BYTES;
+  static constexpr size_t SMEM_BYTES = OFF_CTL + 1024 /* control block: G * sizeof(GroupCtl) + locks */;
   static constexpr int BOX_ROWS = L < 256 ? (int)L : 256;   // TMA box limit: 256 per dimension
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
@@ -194,7 +205,9 @@ constexpr int kStoreRing = 16;
 
 struct GroupCtl {            // per-group control block in shared memory
   uint64_t full;             // TMA for the group's next tile has landed
-  uint64_t empty;            // every thread of the group has pulled its samples out of staging
+  uint64_t empty;            // every thread of the group is done with the staging buffer
+  uint64_t full_tab;         // in-place mode: the tile tables of the group's next pass-1 tile have landed
+  uint64_t empty_tab;        // in-place mode: every thread of the group has issued the stores that use them
   WorkItem desc;             // the tile the staging buffer holds / will hold
   int loaded;                // warps of the group that have pulled their samples out of staging (this tile)
   unsigned stored_warps;     // warps of the group that have issued the stores of the current pass-1 tile
@@ -217,14 +230,16 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   if (wi.pass < 0) { mbar_arrive(&ctl->full); return; }
   // (the group's reads of `dst` are ordered before this refill by the empty-mbarrier wait of the caller)
   if (wi.pass == 1) {
-    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + 2 * Cfg::TAB_BYTES);
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + (Cfg::INPLACE ? 0 : 2 * Cfg::TAB_BYTES));
     constexpr int BOX = Cfg::BOX_ROWS;
     const int x = wi.tile * C * 2;  // in scalars of T
 #pragma unroll
     for (int r0 = 0; r0 < (int)Cfg::L; r0 += BOX)
       tma_load_2d_first(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), &ctl->full);
-    bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
-    bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    if constexpr (!Cfg::INPLACE) {
+      bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+      bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    }
   } else {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES);
     const V* src = a.scratch + (size_t)d.slot * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
@@ -234,6 +249,15 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
       bulk_load((unsigned char*)dst + o, (const unsigned char*)src + o,
                 Cfg::TILE_BYTES - o < PIECE ? Cfg::TILE_BYTES - o : PIECE, &ctl->full);
   }
+}
+
+// In-place mode: the tile tables of a pass-1 tile travel on their own mbarrier (single buffer per group).
+template <class Cfg>
+__device__ __forceinline__ void issue_tables(const WorkItem& wi, const FusedArgs<typename Cfg::T>& a,
+                                             cpx<typename Cfg::T>* tab, GroupCtl* ctl) {
+  mbar_arrive_expect_tx(&ctl->full_tab, 2 * Cfg::TAB_BYTES);
+  bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::C * Cfg::R, Cfg::TAB_BYTES, &ctl->full_tab);
+  bulk_load(tab + Cfg::C * Cfg::R, a.tstep + (size_t)wi.tile * Cfg::C * Cfg::R, Cfg::TAB_BYTES, &ctl->full_tab);
 }
 
 // Address of the counter a work item depends on (nullptr: no dependency) and the value it must reach.
@@ -275,10 +299,10 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   // every staging/exchange access becomes a generic LD/ST (seen in the first profile of this kernel).
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* base = smem_raw;
-  V* staging = reinterpret_cast<V*>(base);                                   // [G][C*L]
+  unsigned char* staging = base;                                             // [G][BUF_BYTES]
   unsigned char* exch_pool = base + Cfg::OFF_EX;
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
-  V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][2][2][C*R]
+  V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][TAB_BUFS][2][C*R]
   GroupCtl* ctl_all = reinterpret_cast<GroupCtl*>(base + Cfg::OFF_CTL);
   int* locks = reinterpret_cast<int*>(ctl_all + G);   // one per exchange buffer
 
@@ -287,6 +311,8 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     for (int g = 0; g < G; ++g) {
       mbar_init(&ctl_all[g].full, 1);
       mbar_init(&ctl_all[g].empty, GT);
+      mbar_init(&ctl_all[g].full_tab, 1);
+      mbar_init(&ctl_all[g].empty_tab, GT);
       ctl_all[g].loaded = 0;
       ctl_all[g].stored_warps = 0;
       ctl_all[g].stored_seq = 0;
@@ -314,8 +340,8 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       // the group has emptied its staging buffer, refill it by TMA.
       const int g = pw;
       GroupCtl* ctl = &ctl_all[g];
-      V* stage_g = staging + (size_t)g * C * L;
-      V* tab_g = tabs + (size_t)g * 4 * C * R;
+      V* stage_g = reinterpret_cast<V*>(staging + (size_t)g * Cfg::BUF_BYTES);
+      V* tab_g = tabs + (size_t)g * Cfg::TAB_BUFS * 2 * C * R;
       uint32_t n_p1 = 0;
       unsigned w_next = atomicAdd(queue, 1u);
       for (uint32_t it = 0;; ++it) {
@@ -328,7 +354,17 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
         FB_PTRACE(1);
         if (it > 0) mbar_wait(&ctl->empty, (it - 1) & 1);
         FB_PTRACE(2);
-        issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
+        if constexpr (Cfg::INPLACE) {
+          // the buffer was last written by the group's own (generic-proxy) exchange stores
+          fence_proxy_async();
+          issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g, ctl);
+          if (wi.pass == 1) {
+            if (n_p1 > 0) mbar_wait(&ctl->empty_tab, (n_p1 - 1) & 1);   // the previous pass-1 tile has stored
+            issue_tables<Cfg>(wi, a, tab_g, ctl);
+          }
+        } else {
+          issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
+        }
         FB_PTRACE(3);
         n_p1 += wi.pass == 1;
         if (wi.pass < 0) break;
@@ -371,11 +407,11 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_CONSUMER));
   const int g = tid / GT;
   const int t = tid - g * GT;
-  V* stage_g = staging + (size_t)g * C * L;
-  V* tab_g = tabs + (size_t)g * 4 * C * R;
+  V* stage_g = reinterpret_cast<V*>(staging + (size_t)g * Cfg::BUF_BYTES);
+  V* tab_g = tabs + (size_t)g * Cfg::TAB_BUFS * 2 * C * R;
   GroupCtl* ctl = &ctl_all[g];
   const int bar_id = 1 + g;
-  V* exch = reinterpret_cast<V*>(exch_pool + (size_t)(g % Cfg::EXB) * Cfg::EX_BYTES);
+  V* exch = Cfg::INPLACE ? stage_g : reinterpret_cast<V*>(exch_pool + (size_t)(g % Cfg::EXB) * Cfg::EX_BYTES);
   int* lock = &locks[g % Cfg::EXB];
   constexpr bool kLocked = Cfg::EXB < G;   // several groups share one exchange buffer
   uint32_t k_p1 = 0;   // pass-1 tiles consumed so far by this group: selects the tile-table buffer
@@ -392,7 +428,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     Tile f;
     if (wi.pass == 1) f.template load<false, C, 1>(t, stage_g);        // staging = [n1][C]
     else f.template load<true, 1, N2>(t, stage_g);                     // staging = C contiguous rows
-    mbar_arrive(&ctl->empty);
+    if constexpr (!Cfg::INPLACE) mbar_arrive(&ctl->empty);
     if (wi.pass == 2) {
       // The intermediate rows this tile just consumed are dead: drop them from L2 instead of letting the
       // cache write them back to HBM later (measured: without this ~80% of the intermediate is written
@@ -423,17 +459,23 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     FB_TRACE(4);
     group_sync(bar_id, GT);
     if (wi.pass == 1) f.template gather<false, Lay1>(t, exch); else f.template gather<false, Lay2>(t, exch);
-    group_sync(bar_id, GT);
-    if (kLocked && t == 0) { __threadfence_block(); atomicExch(lock, 0); }
+    if constexpr (Cfg::INPLACE) {
+      mbar_arrive(&ctl->empty);   // the buffer may be refilled once every thread has gathered
+    } else {
+      group_sync(bar_id, GT);
+      if (kLocked && t == 0) { __threadfence_block(); atomicExch(lock, 0); }
+    }
     FB_TRACE(5);
 
     // ---- stage B and the stores ---------------------------------------------------------------------------------
     f.stage_b();
     if (wi.pass == 1) {
-      const V* tb = tab_g + (size_t)(k_p1 & 1) * 2 * C * R;
+      const V* tb = tab_g + (Cfg::INPLACE ? 0 : (size_t)(k_p1 & 1) * 2 * C * R);
+      if constexpr (Cfg::INPLACE) mbar_wait(&ctl->full_tab, k_p1 & 1);
       ++k_p1;
       V* dst = a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C;
       f.template store_factored<N2, 1, 2>(t, dst, tb, tb + C * R);       // intermediate: keep in L2
+      if constexpr (Cfg::INPLACE) mbar_arrive(&ctl->empty_tab);
       // report "stores issued"; the last warp of the group hands the tile to the signaller warp
       __syncwarp();
       if ((t & 31) == 0 && atom_add_acq_rel_cta_shared(&ctl->stored_warps, 1u) == GT / 32 - 1) {

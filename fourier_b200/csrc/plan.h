@@ -169,10 +169,25 @@ cudaError_t launch_fill_input(T* out, unsigned long long first_scalar, size_t co
 template <typename T>
 cudaError_t launch_transpose(const cpx<T>* in, cpx<T>* out, size_t batch, size_t rows, size_t cols, cudaStream_t s);
 template <typename T>
+cudaError_t launch_pack(const cpx<T>* in, cpx<T>* out, size_t batch, size_t rows, size_t cols, size_t ld, size_t ibs,
+                        size_t obs, int twiddle, unsigned long long row0, unsigned long long col0,
+                        unsigned long long n_total, cudaStream_t s);
+template <typename T>
 cudaError_t launch_swap_leading(const cpx<T>* in, cpx<T>* out, size_t a, size_t b, size_t inner, cudaStream_t s);
 template <typename T>
 cudaError_t launch_twiddle_rows(cpx<T>* data, size_t rows, size_t cols, unsigned long long row0,
                                 unsigned long long n_total, bool forward, cudaStream_t s);
+
+// exchange.cu: exchange step of the distributed transform over NVLink peer memory + CUDA-IPC plumbing
+constexpr int kMaxPeers = 16;
+template <typename T>
+cudaError_t launch_exchange(const cpx<T>* in, void* const* outs, int nranks, int me, size_t rows, size_t cb, size_t ld,
+                            size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
+                            unsigned long long n_total, cudaStream_t s);
+cudaError_t peer_alloc(size_t bytes, void** ptr, void* handle64);
+cudaError_t peer_open(const void* handle64, void** ptr);
+cudaError_t peer_close(void* ptr);
+cudaError_t peer_free(void* ptr);
 
 // host math helpers (plan_math.cpp part of plan.cu)
 void host_twiddle(size_t k, size_t n, double* re, double* im);            // exp(-2*pi*i*k/n), long-double accurate

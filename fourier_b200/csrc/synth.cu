@@ -48,6 +48,53 @@ transpose_kernel(const V* __restrict__ in, V* __restrict__ out, size_t rows, siz
     if (c0 + i < cols && r0 + tx < rows) dst[(c0 + i) * rows + r0 + tx] = tile[tx][i];
 }
 
+// Pack step of a pipelined exchange: a batched transpose of column blocks of one row-major matrix with
+// leading dimension ld, optionally fused with the inter-step twiddle of the six-step algorithm:
+//   out[b*obs + c*rows + r] = in[b*ibs + r*ld + c] * w_N^{(row0 + r) * (col0 + b*ibs + c)}     (TW != 0)
+// (b < batch, r < rows, c < cols; TW = 1 forward, 2 inverse/conjugated, 0 no twiddle).  The angle index is
+// reduced exactly mod N in 64-bit integers; each thread evaluates one twiddle and one step with sincospi
+// in double and walks its 4 rows (8 apart) by recurrence, so the kernel stays memory-bound.
+template <typename T, int TW>
+__global__ void __launch_bounds__(256)
+pack_kernel(const cpx<T>* __restrict__ in, cpx<T>* __restrict__ out, size_t rows, size_t cols, size_t ld,
+            size_t ibs, size_t obs, unsigned long long row0, unsigned long long col0, unsigned long long n_total) {
+  using V = cpx<T>;
+  __shared__ V tile[32][33];
+  const size_t b = blockIdx.z;
+  const V* src = in + b * ibs;
+  V* dst = out + b * obs;
+  const size_t c0 = (size_t)blockIdx.x * 32, r0 = (size_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  double wr = 1.0, wi = 0.0, sr = 1.0, si = 0.0;
+  if constexpr (TW != 0) {
+    const unsigned long long cg = (col0 + b * ibs + c0 + tx) % n_total;
+    // 128-bit products are not needed: row index and column index are both < 2^32 for any N <= 2^62 that is
+    // split as N1*N2 with N1, N2 < 2^32 (checked by the launcher)
+    const unsigned long long m0 = ((row0 + r0 + ty) % n_total) * cg % n_total, ms = 8ull * cg % n_total;
+    sincospi(2.0 * (double)m0 / (double)n_total, &wi, &wr);
+    sincospi(2.0 * (double)ms / (double)n_total, &si, &sr);
+    if (TW == 1) { wi = -wi; si = -si; }
+  }
+  for (int i = ty; i < 32; i += 8) {
+    if (r0 + i < rows && c0 + tx < cols) {
+      V v = src[(r0 + i) * ld + c0 + tx];
+      if constexpr (TW != 0) {
+        const double xr = (double)v.x, xi = (double)v.y;
+        v = mk<T>((T)(xr * wr - xi * wi), (T)(xr * wi + xi * wr));
+      }
+      tile[i][tx] = v;
+    }
+    if constexpr (TW != 0) {
+      const double nr = wr * sr - wi * si;
+      wi = wr * si + wi * sr;
+      wr = nr;
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    if (c0 + i < cols && r0 + tx < rows) dst[(c0 + i) * rows + r0 + tx] = tile[tx][i];
+}
+
 // out[b][a][i] = in[a][b][i]: swaps the two leading axes of a 3-D array whose innermost runs (i < inner)
 // stay contiguous -- the unpack step after an all-to-all (received [src rank][my row][their rows]).
 template <typename V>
@@ -88,6 +135,24 @@ cudaError_t launch_transpose(const cpx<T>* in, cpx<T>* out, size_t batch, size_t
   transpose_kernel<cpx<T>><<<grid, 256, 0, s>>>(in, out, rows, cols);
   return cudaGetLastError();
 }
+template <typename T>
+cudaError_t launch_pack(const cpx<T>* in, cpx<T>* out, size_t batch, size_t rows, size_t cols, size_t ld, size_t ibs,
+                        size_t obs, int twiddle, unsigned long long row0, unsigned long long col0,
+                        unsigned long long n_total, cudaStream_t s) {
+  if (batch == 0 || rows == 0 || cols == 0) return cudaSuccess;
+  if (batch > 65535 || (rows + 31) / 32 > 65535 || twiddle < 0 || twiddle > 2) return cudaErrorInvalidValue;
+  if (twiddle != 0 && (n_total == 0 || row0 + rows > (1ull << 32) || col0 + (batch - 1) * ibs + cols > (1ull << 32)))
+    return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batch);
+  if (twiddle == 0) pack_kernel<T, 0><<<grid, 256, 0, s>>>(in, out, rows, cols, ld, ibs, obs, row0, col0, n_total);
+  else if (twiddle == 1) pack_kernel<T, 1><<<grid, 256, 0, s>>>(in, out, rows, cols, ld, ibs, obs, row0, col0, n_total);
+  else pack_kernel<T, 2><<<grid, 256, 0, s>>>(in, out, rows, cols, ld, ibs, obs, row0, col0, n_total);
+  return cudaGetLastError();
+}
+template cudaError_t launch_pack<float>(const cpx<float>*, cpx<float>*, size_t, size_t, size_t, size_t, size_t, size_t,
+                                        int, unsigned long long, unsigned long long, unsigned long long, cudaStream_t);
+template cudaError_t launch_pack<double>(const cpx<double>*, cpx<double>*, size_t, size_t, size_t, size_t, size_t, size_t,
+                                         int, unsigned long long, unsigned long long, unsigned long long, cudaStream_t);
 template <typename T>
 cudaError_t launch_swap_leading(const cpx<T>* in, cpx<T>* out, size_t a, size_t b, size_t inner, cudaStream_t s) {
   size_t blocks = (a * b * inner + 255) / 256;

@@ -102,17 +102,31 @@ template <class Cfg> struct FusedImpl {
 };
 
 template <typename T> const FusedOps<T>* fused_lookup(size_t n);
+// FOURIER_B200_CFG selects an alternative configuration of the persistent kernel (experiments; 0 = default).
 template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
   if (n == ((size_t)1 << 20)) {
-    // FOURIER_B200_TILE=4: four 128-thread groups on 4-column tiles (one warp of each group per SM
-    // sub-partition), two exchange buffers; default: two 256-thread groups on 8-column tiles
-    if (env_int("FOURIER_B200_TILE", 8) == 4) return FusedImpl<fused::FusedCfg<float, 32, 4, 4, 4, 2>>::ops(8, 4);
-    return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
+    switch (env_int("FOURIER_B200_CFG", 0)) {
+      // two 256-thread groups on 8-column tiles, one shared exchange buffer taken under a lock
+      case 1: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
+      // four 128-thread groups on 4-column tiles, two exchange buffers
+      case 2: return FusedImpl<fused::FusedCfg<float, 32, 4, 4, 4, 2>>::ops(8, 4);
+      // exchange in place in the staging buffer: two groups / three groups
+      case 3: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 0>>::ops(8, 4);
+      case 4: return FusedImpl<fused::FusedCfg<float, 32, 8, 3, 8, 0>>::ops(16, 6);
+      default: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
+    }
   }
   return nullptr;
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
-  if (n == ((size_t)1 << 16)) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
+  if (n == ((size_t)1 << 16)) {
+    switch (env_int("FOURIER_B200_CFG", 0)) {
+      case 1: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
+      case 3: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 0>>::ops(64, 32);
+      case 4: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 0>>::ops(128, 48);
+      default: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
+    }
+  }
   return nullptr;
 }
 
@@ -214,7 +228,7 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
       FB_CHECK(cudaStreamSynchronize(s));
       FB_CHECK(cudaMemcpy(h.data(), trace_.data(), h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
       if (FILE* fp = fopen(std::getenv("FOURIER_B200_TRACE"), "w")) {
-        for (int w = 0; w < 20; ++w)
+        for (int w = 0; w < 40; ++w)
           for (int k = 0; k < fused::kTraceTiles; ++k) {
             const long long* r = &h[((size_t)w * fused::kTraceTiles + k) * fused::kTracePhases];
             fprintf(fp, "%d %d %lld %lld %lld %lld %lld %lld %lld %lld\n", w, k, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);

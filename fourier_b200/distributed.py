@@ -8,17 +8,30 @@ Layout.  N = N1*N2.  The input is block-distributed in natural order: rank r of 
 [r*N/P, (r+1)*N/P), i.e. rows n1 in [r*N1/P, (r+1)*N1/P) of x[n1][n2] (n = n1*N2 + n2).  The output has the
 same block distribution of natural order X[k], k = k1 + N1*k2: rank r holds rows k2 of X[k2][k1].
 
-    1. exchange:  [n1_loc][n2]  ->  [n2_loc][n1]
-    2. N2/P local FFTs of length N1 over n1, then  *= w_N^{n2*k1}
-    3. exchange:  [n2_loc][k1]  ->  [k1_loc][n2]
-    4. N1/P local FFTs of length N2 over n2
-    5. exchange:  [k1_loc][k2]  ->  [k2_loc][k1]      (natural order)
+    1. exchange:  [n1_loc][n2]  ->  [n2_loc][n1],  N2/P local FFTs of length N1 over n1
+    2. exchange:  [n2_loc][k1] * w_N^{n2*k1}  ->  [k1_loc][n2],  N1/P local FFTs of length N2 over n2
+    3. exchange:  [k1_loc][k2]  ->  [k2_loc][k1]      (natural order)
 
-One exchange = the transpose of a row-distributed matrix: local transpose (the block for rank q becomes
-contiguous), one `all_to_all_single` of N/P samples per rank (N/P * (P-1)/P cross NVLink), local swap of
-the two leading axes of the received [source rank][my rows][their rows].  The local pieces are this
-library's kernels (batched FFT plans, fourier_b200_transpose_*, _swap_leading_*, _twiddle_rows_*);
-torch provides memory, streams and the collective.
+One exchange = the transpose of a row-distributed matrix, pipelined in `chunks` pieces over the rows of the
+RESULT (each piece holds complete result rows, so the work that follows can start on it):
+
+    pack     local transpose of the piece's column blocks, so that what goes to rank q is contiguous
+             (fourier_b200_pack_*; in exchange 2 the inter-step twiddle is applied on the way)
+    send     one asynchronous all_to_all_single per piece: N/P/chunks samples per rank, (P-1)/P of them
+             over NVLink; the collective of piece k runs while piece k+1 is packed and piece k-1 is
+             unpacked and transformed
+    unpack   swap of the two leading axes of the received [source rank][my rows][their rows]
+             (fourier_b200_swap_leading_*) straight into the piece's rows of the result
+    then     the local FFTs of those rows (fourier_b200_transform_batch_async_*)
+
+With exchange="peer" (CudaBackend only) the three sweeps of an exchange collapse into ONE kernel
+(fourier_b200_exchange_*, csrc/exchange.cu): the transposing kernel stores its tiles straight into the
+destination rank's buffer over NVLink, already in the final layout, with the twiddle applied on the way;
+a stream-ordered barrier (a one-element all_reduce) separates it from the FFTs that follow.  The two
+work buffers then come from `plan.buffers()`: they are cudaMalloc'ed by the library and opened by every
+peer through CUDA IPC (one process per GPU).
+
+The local pieces are this library's kernels; torch provides memory, streams and the collective.
 
 `backend` abstracts the local compute so that the exchange logic is tested on CPU with gloo + numpy
 (tests/test_distributed_host_logic.py); the product backend is `CudaBackend` (no CPU fallback).
@@ -47,6 +60,12 @@ class CudaBackend:
         if rc != 0:
             raise RuntimeError(f"fourier_b200_{name}_{self.t} failed: {_lib.last_error()}")
 
+    def empty_like(self, x):
+        return self.torch.empty_like(x)
+
+    def empty(self, samples):
+        return self.torch.empty(samples, dtype=self.dtype, device="cuda")
+
     def fft_rows(self, x, n, forward):
         """In-place batched FFT over rows of length n (unscaled in both directions)."""
         from . import Fft, Transform
@@ -58,16 +77,83 @@ class CudaBackend:
     def transpose(self, src, dst, rows, cols):
         self._call("transpose", src.data_ptr(), dst.data_ptr(), 1, rows, cols, self._stream(src))
 
+    def pack(self, src, dst, batch, rows, cols, ld, col0, twiddle):
+        """dst[b][c][r] = src[r][col0 + b*(ld/batch) + c] (* twiddle), src row-major with `ld` columns.
+        twiddle = None or (forward, row0, n_total): factor w_N^{(row0 + r) * column}."""
+        mode, row0, n_total = (0, 0, 0) if twiddle is None else (1 if twiddle[0] else 2, twiddle[1], twiddle[2])
+        item = src.element_size()
+        self._call("pack", src.data_ptr() + col0 * item, dst.data_ptr(), batch, rows, cols, ld, ld // batch,
+                   cols * rows, mode, row0, col0, n_total, self._stream(src))
+
     def swap_leading(self, src, dst, a, b, inner):
         self._call("swap_leading", src.data_ptr(), dst.data_ptr(), a, b, inner, self._stream(src))
 
     def twiddle_rows(self, x, rows, cols, row0, n_total, forward):
         self._call("twiddle_rows", x.data_ptr(), rows, cols, row0, n_total, int(forward), self._stream(x))
 
+    # ---- exchange over NVLink peer memory ------------------------------------------------------------------
+    def peer_buffers(self, samples, count, rank, world, group):
+        """Collective.  Allocates `count` buffers of `samples` complex values that every rank of the group can
+        store into; returns (tensors, tables): tables[i][q] is the address of rank q's buffer i on this GPU."""
+        import ctypes
+        import torch.distributed as dist
+        L = _lib.load()
+        item = 8 if self.real == "f32" else 16
+        mine = []
+        for _ in range(count):
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            if L.fourier_b200_peer_alloc(samples * item, ctypes.byref(ptr), handle) != 0:
+                raise RuntimeError(f"fourier_b200_peer_alloc failed: {_lib.last_error()}")
+            mine.append((ptr.value, handle.raw))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, [h for _, h in mine], group=group)
+        tensors, tables = [], []
+        for i, (ptr, _) in enumerate(mine):
+            table = (ctypes.c_void_p * world)()
+            for q in range(world):
+                if q == rank:
+                    table[q] = ptr
+                else:
+                    peer = ctypes.c_void_p()
+                    if L.fourier_b200_peer_open(everyone[q][i], ctypes.byref(peer)) != 0:
+                        raise RuntimeError(f"fourier_b200_peer_open failed: {_lib.last_error()}")
+                    table[q] = peer.value
+            tensors.append(_as_complex_tensor(self.torch, ptr, samples, self.real))
+            tables.append(table)
+        self._token = self.torch.zeros(1, device="cuda")
+        return tensors, tables
+
+    def exchange(self, src, table, world, rank, rows_loc, cb, twiddle):
+        mode, row0, n_total = (0, 0, 0) if twiddle is None else (1 if twiddle[0] else 2, twiddle[1], twiddle[2])
+        self._call("exchange", src.data_ptr(), table, world, rank, rows_loc, cb, world * cb, world * rows_loc,
+                   rank * rows_loc, mode, row0, n_total, self._stream(src))
+
+    def barrier(self, group):
+        """Stream-ordered (no host synchronisation): every rank's earlier kernels have completed, and with them
+        their stores into peer memory, before any rank's later kernels start."""
+        import torch.distributed as dist
+        dist.all_reduce(self._token, group=group)
+
     def all_to_all(self, dst, src, group):
+        """Asynchronous: ordered after the work already enqueued on the current stream; returns a handle
+        whose wait() makes the current stream (not the host) wait for the collective."""
         import torch.distributed as dist
         # NCCL has no complex dtype: exchange the raw (re, im) scalars
-        dist.all_to_all_single(self.torch.view_as_real(dst), self.torch.view_as_real(src), group=group)
+        return dist.all_to_all_single(self.torch.view_as_real(dst), self.torch.view_as_real(src), group=group,
+                                      async_op=True)
+
+
+class _DeviceMemory:
+    """A library-owned device allocation seen through the CUDA array interface."""
+
+    def __init__(self, ptr, scalars, real):
+        self.__cuda_array_interface__ = {"shape": (scalars,), "typestr": "<f4" if real == "f32" else "<f8",
+                                         "data": (ptr, False), "version": 2}
+
+
+def _as_complex_tensor(torch, ptr, samples, real):
+    flat = torch.as_tensor(_DeviceMemory(ptr, 2 * samples, real), device="cuda")
+    return torch.view_as_complex(flat.view(samples, 2))
 
 
 class NumpyBackend:
@@ -77,12 +163,30 @@ class NumpyBackend:
         import torch
         self.torch = torch
 
+    def empty_like(self, x):
+        return self.torch.empty_like(x)
+
+    def empty(self, samples):
+        return self.torch.empty(samples, dtype=self.torch.complex128)
+
     def fft_rows(self, x, n, forward):
         a = x.view(-1, n).numpy()
         a[...] = np.fft.fft(a, axis=-1) if forward else np.fft.ifft(a, axis=-1) * n
 
     def transpose(self, src, dst, rows, cols):
         dst.view(cols, rows).copy_(src.view(rows, cols).t())
+
+    def pack(self, src, dst, batch, rows, cols, ld, col0, twiddle):
+        a = src.view(rows, ld).numpy()
+        out = dst.view(batch, cols, rows).numpy()
+        for b in range(batch):
+            c = col0 + b * (ld // batch) + np.arange(cols, dtype=np.int64)
+            blk = a[:, c]
+            if twiddle is not None:
+                forward, row0, n_total = twiddle
+                idx = (np.arange(rows, dtype=np.int64)[:, None] + row0) * c[None, :] % n_total
+                blk = blk * np.exp((-2j if forward else 2j) * np.pi * idx / n_total).astype(a.dtype)
+            out[b] = blk.T
 
     def swap_leading(self, src, dst, a, b, inner):
         dst.view(b, a, inner).copy_(src.view(a, b, inner).transpose(0, 1))
@@ -95,17 +199,35 @@ class NumpyBackend:
 
     def all_to_all(self, dst, src, group):
         import torch.distributed as dist
-        dist.all_to_all_single(self.torch.view_as_real(dst), self.torch.view_as_real(src), group=group)
+        return dist.all_to_all_single(self.torch.view_as_real(dst), self.torch.view_as_real(src), group=group,
+                                      async_op=True)
 
 
 class DistributedFft:
-    """Plan for one length-N transform over `world` ranks (N = n1 * n2, both divisible by world)."""
+    """Plan for one length-N transform over `world` ranks (N = n1 * n2, both divisible by world).
+    `chunks` pieces per exchange (reduced to a divisor of the rows each rank receives)."""
 
-    def __init__(self, n1, n2, rank, world, backend, group=None):
+    def __init__(self, n1, n2, rank, world, backend, group=None, chunks=4, exchange="nccl"):
         if n1 % world or n2 % world:
             raise ValueError("n1 and n2 must be divisible by the number of ranks")
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
         self.n1, self.n2, self.n = n1, n2, n1 * n2
         self.rank, self.world, self.backend, self.group = rank, world, backend, group
+        self.chunks = max(1, int(chunks))
+        self.exchange = exchange if world > 1 else "nccl"
+        self._send = self._recv = None
+        self._bufs, self._tables = None, {}
+        if self.exchange == "peer":      # collective: every rank of the group constructs the plan
+            self._bufs, tables = backend.peer_buffers(self.local_samples(), 2, rank, world, group)
+            self._tables = {b.data_ptr(): t for b, t in zip(self._bufs, tables)}
+            backend.barrier(group)
+
+    def buffers(self):
+        """The two work buffers to pass to transform(): peer-visible memory with exchange="peer"."""
+        if self._bufs is None:
+            self._bufs = [self.backend.empty(self.local_samples()) for _ in range(2)]
+        return self._bufs
 
     def local_samples(self):
         return self.n // self.world
@@ -114,16 +236,51 @@ class DistributedFft:
         """Bytes each rank sends over NVLink per exchange."""
         return self.local_samples() * itemsize * (self.world - 1) // self.world
 
-    def _exchange(self, src, dst, rows_loc, cols):
-        """Transpose of the row-distributed global matrix [rows_loc * P][cols]: on return `dst` holds this
-        rank's [cols / P] rows of the transposed matrix, each rows_loc * P long.  `src` is clobbered."""
+    def _pieces(self, rows_out):
+        k = min(self.chunks, rows_out)
+        while rows_out % k:
+            k -= 1
+        return k
+
+    def _exchange(self, src, dst, rows_loc, cols, twiddle=None, then=None):
+        """Transpose of the row-distributed global matrix [rows_loc * P][cols] (times the twiddle, if given):
+        on return `dst` holds this rank's cols / P rows of the transposed matrix, each rows_loc * P long,
+        and `then(rows, first_row)` has been applied to every piece of them.  `src` is left intact."""
         P, be = self.world, self.backend
-        cb = cols // P
-        be.transpose(src, dst, rows_loc, cols)              # dst = [cols][rows_loc] = [P][cb][rows_loc]
-        if P == 1:
+        cb = cols // P                                  # result rows of this rank
+        if self.exchange == "peer":
+            table = self._tables.get(dst.data_ptr())
+            if table is None:
+                raise ValueError("exchange='peer': transform() needs the plan's own buffers (plan.buffers())")
+            be.exchange(src, table, P, self.rank, rows_loc, cb, twiddle)
+            be.barrier(self.group)
+            if then:
+                then(dst, 0)
             return dst
-        be.all_to_all(src, dst, self.group)                 # src = [P (source rank)][cb][rows_loc]
-        be.swap_leading(src, dst, P, cb, rows_loc)          # dst = [cb][P][rows_loc] = [cb][rows_loc * P]
+        if P == 1:
+            if twiddle is None:
+                be.transpose(src, dst, rows_loc, cols)
+            else:
+                be.pack(src, dst, 1, rows_loc, cols, cols, 0, twiddle)
+            if then:
+                then(dst, 0)
+            return dst
+        if self._send is None or self._send.numel() != src.numel() or self._send.dtype != src.dtype:
+            self._send, self._recv = be.empty_like(src), be.empty_like(src)
+        K = self._pieces(cb)
+        cbk = cb // K
+        piece = P * cbk * rows_loc                      # samples per piece, on every side
+        work = []
+        for k in range(K):
+            s = self._send[k * piece:(k + 1) * piece]
+            be.pack(src, s, P, rows_loc, cbk, cols, k * cbk, twiddle)          # [P][cbk][rows_loc]
+            work.append(be.all_to_all(self._recv[k * piece:(k + 1) * piece], s, self.group))
+        for k in range(K):
+            work[k].wait()
+            d = dst[k * piece:(k + 1) * piece]                                 # rows k*cbk .. of the result
+            be.swap_leading(self._recv[k * piece:(k + 1) * piece], d, P, cbk, rows_loc)   # [cbk][P * rows_loc]
+            if then:
+                then(d, k * cbk)
         return dst
 
     def transform(self, x, scratch, forward=True):
@@ -133,11 +290,7 @@ class DistributedFft:
         P, be = self.world, self.backend
         n1, n2 = self.n1, self.n2
         r1, r2 = n1 // P, n2 // P
-        a = self._exchange(x, scratch, r1, n2)              # [n2_loc][n1]
-        b = x if a is scratch else scratch
-        be.fft_rows(a, n1, forward)
-        be.twiddle_rows(a, r2, n1, self.rank * r2, self.n, forward)
-        b = self._exchange(a, b, r2, n1)                    # [k1_loc][n2]
-        a = x if b is scratch else scratch
-        be.fft_rows(b, n2, forward)
-        return self._exchange(b, a, r1, n2)                 # [k2_loc][k1]
+        a = self._exchange(x, scratch, r1, n2, then=lambda rows, first: be.fft_rows(rows, n1, forward))   # [n2_loc][k1]
+        b = self._exchange(a, x, r2, n1, twiddle=(forward, self.rank * r2, self.n),
+                           then=lambda rows, first: be.fft_rows(rows, n2, forward))                       # [k1_loc][k2]
+        return self._exchange(b, scratch, r1, n2)                                                         # [k2_loc][k1]

@@ -85,6 +85,32 @@ int fourier_b200_transpose_float(const void *in_dev, void *out_dev, size_t batch
                                  void *cuda_stream);
 int fourier_b200_transpose_double(const void *in_dev, void *out_dev, size_t batch, size_t rows, size_t cols,
                                   void *cuda_stream);
+/* Pack step of a pipelined exchange: batched transpose of column blocks of a row-major matrix with leading
+ * dimension ld, optionally fused with the inter-step twiddle (twiddle = 0 none, 1 forward, 2 inverse):
+ *   out[b*out_batch_stride + c*rows + r] = in[b*in_batch_stride + r*ld + c] * w_N^{(row0+r)*(col0+b*in_batch_stride+c)} */
+int fourier_b200_pack_float(const void *in_dev, void *out_dev, size_t batch, size_t rows, size_t cols, size_t ld,
+                            size_t in_batch_stride, size_t out_batch_stride, int twiddle, unsigned long long row0,
+                            unsigned long long col0, unsigned long long n_total, void *cuda_stream);
+int fourier_b200_pack_double(const void *in_dev, void *out_dev, size_t batch, size_t rows, size_t cols, size_t ld,
+                             size_t in_batch_stride, size_t out_batch_stride, int twiddle, unsigned long long row0,
+                             unsigned long long col0, unsigned long long n_total, void *cuda_stream);
+/* The whole exchange as ONE kernel over NVLink peer memory: rank `me` of `nranks` holds `rows` rows of
+ * ld = nranks*cb columns and stores columns [q*cb, (q+1)*cb) transposed into rank q's buffer outs[q]
+ * (device pointers valid on this GPU: own memory for q == me, fourier_b200_peer_open()ed memory otherwise):
+ *   outs[q][out_off + c*out_ld + r] = in[r*ld + q*cb + c] * w_N^{(row0+r)*(q*cb+c)}      (twiddle as above)
+ * `outs` is a HOST array of nranks pointers.  The caller orders ranks with a stream-ordered barrier. */
+int fourier_b200_exchange_float(const void *in_dev, void *const *outs, int nranks, int me, size_t rows, size_t cb,
+                                size_t ld, size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
+                                unsigned long long n_total, void *cuda_stream);
+int fourier_b200_exchange_double(const void *in_dev, void *const *outs, int nranks, int me, size_t rows, size_t cb,
+                                 size_t ld, size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
+                                 unsigned long long n_total, void *cuda_stream);
+/* Buffers other ranks of the box (one process per GPU) can store into: cudaMalloc + CUDA IPC.  `handle64` is
+ * the 64-byte cudaIpcMemHandle_t to send to the peers (any transport), who open it with _peer_open. */
+int fourier_b200_peer_alloc(size_t bytes, void **dev_ptr, void *handle64);
+int fourier_b200_peer_open(const void *handle64, void **dev_ptr);
+int fourier_b200_peer_close(void *dev_ptr);
+int fourier_b200_peer_free(void *dev_ptr);
 /* out[b][a][i] = in[a][b][i] (i < inner contiguous): unpack step after an all-to-all */
 int fourier_b200_swap_leading_float(const void *in_dev, void *out_dev, size_t a, size_t b, size_t inner,
                                     void *cuda_stream);

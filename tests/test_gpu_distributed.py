@@ -36,3 +36,51 @@ def test_transpose_and_swap_kernels():
     assert torch.equal(out.view(3, 45, 70), a.view(3, 70, 45).transpose(1, 2))
     be.swap_leading(a, out, 3, 70, 45)
     assert torch.equal(out.view(70, 3, 45), a.view(3, 70, 45).transpose(0, 1))
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("twiddle", [None, (True, 37, 1 << 30), (False, 5, 3 * 70 * 96)])
+def test_pack_kernel_matches_numpy_backend(real, twiddle):
+    """Strided batched transpose (+ fused inter-step twiddle) against the CPU stand-in of the host tests."""
+    import torch
+    from fourier_b200.distributed import CudaBackend, NumpyBackend
+    dt = torch.complex64 if real == "f32" else torch.complex128
+    batch, rows, cols, ld, col0 = 3, 70, 20, 96, 9          # column blocks [9, 29), [41, 61), [73, 93) of 96
+    torch.manual_seed(5)
+    a = torch.randn(rows * ld, dtype=dt)
+    want = torch.empty(batch * cols * rows, dtype=dt)
+    NumpyBackend().pack(a, want, batch, rows, cols, ld, col0, twiddle)
+    got = torch.empty_like(want).cuda()
+    CudaBackend(real).pack(a.cuda(), got, batch, rows, cols, ld, col0, twiddle)
+    torch.cuda.synchronize()
+    assert rel_err(got.cpu().numpy(), want.numpy()) < (5e-7 if real == "f32" else 4e-15)
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+@pytest.mark.parametrize("forward", [None, True, False])
+def test_peer_exchange_kernel_layout(real, forward):
+    """The one-kernel exchange with the P destination buffers all on this GPU: rank by rank it must build, in
+    every destination, that rank's rows of the transposed (and twiddled) global matrix."""
+    import ctypes
+    import torch
+    from fourier_b200.distributed import CudaBackend
+    P, rows_loc, cb = 4, 40, 24
+    cols, n_total = P * cb, P * rows_loc * P * cb
+    dt = torch.complex64 if real == "f32" else torch.complex128
+    torch.manual_seed(11)
+    g = torch.randn(P * rows_loc, cols, dtype=torch.complex128)
+    if forward is not None:
+        idx = (torch.arange(P * rows_loc)[:, None] * torch.arange(cols)[None, :]) % n_total
+        w = torch.exp((-2j if forward else 2j) * np.pi * idx.to(torch.float64) / n_total)
+    else:
+        w = torch.ones_like(g)
+    outs = [torch.zeros(cb * P * rows_loc, dtype=dt, device="cuda") for _ in range(P)]
+    table = (ctypes.c_void_p * P)(*[o.data_ptr() for o in outs])
+    be = CudaBackend(real)
+    for me in range(P):
+        src = g[me * rows_loc:(me + 1) * rows_loc].to(dt).contiguous().cuda()
+        be.exchange(src, table, P, me, rows_loc, cb, None if forward is None else (forward, me * rows_loc, n_total))
+    torch.cuda.synchronize()
+    for q in range(P):
+        want = (g * w)[:, q * cb:(q + 1) * cb].t().contiguous().numpy().ravel()
+        assert rel_err(outs[q].cpu().numpy(), want) < (5e-7 if real == "f32" else 4e-15)

@@ -220,6 +220,22 @@ def test_fused_paths_agree_with_general_path(real, n):
         assert rel_err(gpu_transform(fast, x, code), gpu_transform(gen, x, code)) < TOL[real]
 
 
+@pytest.mark.parametrize("real,n", [("f32", 1 << 20), ("f64", 1 << 16)])
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
+def test_alternative_persistent_kernel_configurations(monkeypatch, real, n, cfg):
+    # FOURIER_B200_CFG (read when the plan is created) selects the experimental variants of the persistent
+    # two-pass kernel: shared/own exchange buffers, exchange in place, 2..4 consumer groups
+    monkeypatch.setenv("FOURIER_B200_CFG", str(cfg))
+    x = O.fill_input(40, n, NP[real], first_transform=2)
+    alt = create(real, n)
+    monkeypatch.delenv("FOURIER_B200_CFG")
+    ref = create(real, n)
+    for code in (T.Fft, T.Ifft):
+        got = gpu_transform(alt, x, code)
+        assert rel_err(got, gpu_transform(ref, x, code)) < TOL[real]
+        assert rel_err(got[7], O.transform(x[7], int(code))) < TOL[real]
+
+
 def test_error_conventions():
     L = _lib.load()
     assert not L.fourier_create_float(0)          # reference hangs on 0 (autosort/mod.rs:112): refused
