@@ -172,7 +172,7 @@ def run_distributed(args, rank, local_rank, world, barrier):
     n1, n2 = 1 << (k // 2), 1 << (k - k // 2)
     n = n1 * n2
     blk = n // world
-    plan = DistributedFft(n1, n2, rank, world, CudaBackend("f32"), exchange=args.exchange)
+    plan = DistributedFft(n1, n2, rank, world, CudaBackend("f32"), exchange=args.exchange, chunks=args.chunks or None)
     x, s = plan.buffers()
     fb.fill_input(x.view(1, blk), first_transform=rank)
     cur, oth = x, s
@@ -209,7 +209,8 @@ def run_distributed(args, rank, local_rank, world, barrier):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS["c5"][3], "N": n, "n1": n1, "n2": n2,
                    "parallelism": (f"block-distributed over {world} ranks, 3 exchanges, each ONE transposing kernel storing "
-                                   "into the peers' buffers over NVLink (CUDA IPC) + a stream-ordered barrier"
+                                   "into the peers' buffers over NVLink (CUDA IPC) + a stream-ordered barrier; the "
+                                   f"exchange of a row block overlaps the FFTs of the next ({plan.chunks} blocks)"
                                    if plan.exchange == "peer" else
                                    f"block-distributed over {world} ranks, 3 NCCL all-to-all transposes, each "
                                    f"pipelined in {plan.chunks} pieces"),
@@ -237,6 +238,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--verify", type=int, default=4, help="transforms checked against the oracle")
     ap.add_argument("--log2n", type=int, default=30, help="c5 only: log2 of the distributed transform length")
+    ap.add_argument("--chunks", type=int, default=0, help="c5 only: row blocks per pipelined exchange (0 = plan default)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="c5 only: exchanges as one kernel over NVLink peer memory, or pack + NCCL all_to_all + unpack")
     args = ap.parse_args()

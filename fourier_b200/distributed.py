@@ -123,10 +123,19 @@ class CudaBackend:
         self._token = self.torch.zeros(1, device="cuda")
         return tensors, tables
 
-    def exchange(self, src, table, world, rank, rows_loc, cb, twiddle):
+    def exchange(self, src, table, world, rank, rows_loc, cb, twiddle, first=0, count=None):
+        """Rows [first, first + count) of this rank's rows_loc x (world * cb) matrix `src` go, transposed, into
+        the peers' buffers (table[q]); twiddle = None or (forward, global index of local row 0, N)."""
+        count = rows_loc - first if count is None else count
         mode, row0, n_total = (0, 0, 0) if twiddle is None else (1 if twiddle[0] else 2, twiddle[1], twiddle[2])
-        self._call("exchange", src.data_ptr(), table, world, rank, rows_loc, cb, world * cb, world * rows_loc,
-                   rank * rows_loc, mode, row0, n_total, self._stream(src))
+        ld = world * cb
+        self._call("exchange", src.data_ptr() + first * ld * src.element_size(), table, world, rank, count, cb, ld,
+                   world * rows_loc, rank * rows_loc + first, mode, row0 + first, n_total, self._stream(src))
+
+    def side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = self.torch.cuda.Stream()
+        return self._side
 
     def barrier(self, group):
         """Stream-ordered (no host synchronisation): every rank's earlier kernels have completed, and with them
@@ -205,17 +214,20 @@ class NumpyBackend:
 
 class DistributedFft:
     """Plan for one length-N transform over `world` ranks (N = n1 * n2, both divisible by world).
-    `chunks` pieces per exchange (reduced to a divisor of the rows each rank receives)."""
+    `chunks` pieces per exchange (reduced to a divisor of the rows each rank receives; None = the measured best
+    of the exchange mode)."""
 
-    def __init__(self, n1, n2, rank, world, backend, group=None, chunks=4, exchange="nccl"):
+    def __init__(self, n1, n2, rank, world, backend, group=None, chunks=None, exchange="nccl"):
         if n1 % world or n2 % world:
             raise ValueError("n1 and n2 must be divisible by the number of ranks")
         if exchange not in ("nccl", "peer"):
             raise ValueError("exchange must be 'nccl' or 'peer'")
         self.n1, self.n2, self.n = n1, n2, n1 * n2
         self.rank, self.world, self.backend, self.group = rank, world, backend, group
-        self.chunks = max(1, int(chunks))
         self.exchange = exchange if world > 1 else "nccl"
+        # measured (profiles/r01_c5_variants_8gpu.json, r01_c5_breakdown.txt): 8 pieces is the best pipelining of
+        # the NCCL formulation; on the peer-memory path the overlap gains nothing yet (1 = no pipelining)
+        self.chunks = max(1, int(chunks)) if chunks else (1 if self.exchange == "peer" else 8)
         self._send = self._recv = None
         self._bufs, self._tables = None, {}
         if self.exchange == "peer":      # collective: every rank of the group constructs the plan
@@ -248,15 +260,6 @@ class DistributedFft:
         and `then(rows, first_row)` has been applied to every piece of them.  `src` is left intact."""
         P, be = self.world, self.backend
         cb = cols // P                                  # result rows of this rank
-        if self.exchange == "peer":
-            table = self._tables.get(dst.data_ptr())
-            if table is None:
-                raise ValueError("exchange='peer': transform() needs the plan's own buffers (plan.buffers())")
-            be.exchange(src, table, P, self.rank, rows_loc, cb, twiddle)
-            be.barrier(self.group)
-            if then:
-                then(dst, 0)
-            return dst
         if P == 1:
             if twiddle is None:
                 be.transpose(src, dst, rows_loc, cols)
@@ -283,6 +286,37 @@ class DistributedFft:
                 then(d, k * cbk)
         return dst
 
+    def _fft_then_exchange(self, src, dst, rows_loc, cols, fft_len, forward, twiddle):
+        """Peer mode: the local FFTs over the rows of `src` and the exchange that follows them, software-
+        pipelined over `chunks` row blocks: while block k travels over NVLink (side stream) block k+1 is being
+        transformed (current stream).  A row of `src` is a complete FFT, so its exchange can start as soon as
+        its block is done; the receivers need every block of every rank, hence one barrier at the end."""
+        be, torch = self.backend, self.backend.torch
+        table = self._table(dst)
+        K = self._pieces(rows_loc) if fft_len else 1
+        rows_k = rows_loc // K
+        main, side = torch.cuda.current_stream(), be.side_stream()
+        for k in range(K):
+            if fft_len:
+                be.fft_rows(src[k * rows_k * cols:(k + 1) * rows_k * cols], fft_len, forward)
+            if K == 1:
+                be.exchange(src, table, self.world, self.rank, rows_loc, cols // self.world, twiddle)
+                break
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                be.exchange(src, table, self.world, self.rank, rows_loc, cols // self.world, twiddle,
+                            first=k * rows_k, count=rows_k)
+        if K > 1:
+            main.wait_stream(side)
+        be.barrier(self.group)
+        return dst
+
+    def _table(self, dst):
+        table = self._tables.get(dst.data_ptr())
+        if table is None:
+            raise ValueError("exchange='peer': transform() needs the plan's own buffers (plan.buffers())")
+        return table
+
     def transform(self, x, scratch, forward=True):
         """x: this rank's N/P samples (its block of the natural order), scratch: same size.  Both are
         clobbered; returns the one holding this rank's block of the result (unscaled in both directions:
@@ -290,6 +324,10 @@ class DistributedFft:
         P, be = self.world, self.backend
         n1, n2 = self.n1, self.n2
         r1, r2 = n1 // P, n2 // P
+        if self.exchange == "peer":
+            a = self._fft_then_exchange(x, scratch, r1, n2, 0, forward, None)                          # [n2_loc][n1]
+            b = self._fft_then_exchange(a, x, r2, n1, n1, forward, (forward, self.rank * r2, self.n))  # [k1_loc][n2]
+            return self._fft_then_exchange(b, scratch, r1, n2, n2, forward, None)                      # [k2_loc][k1]
         a = self._exchange(x, scratch, r1, n2, then=lambda rows, first: be.fft_rows(rows, n1, forward))   # [n2_loc][k1]
         b = self._exchange(a, x, r2, n1, twiddle=(forward, self.rank * r2, self.n),
                            then=lambda rows, first: be.fft_rows(rows, n2, forward))                       # [k1_loc][k2]
