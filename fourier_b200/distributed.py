@@ -123,6 +123,16 @@ class CudaBackend:
         self._token = self.torch.zeros(1, device="cuda")
         return tensors, tables
 
+    def peer_release(self, tensors, tables, rank):
+        """Closes the peers' mappings and frees this rank's buffers (the tensors must not be used afterwards)."""
+        L = _lib.load()
+        self.torch.cuda.synchronize()
+        for t, table in zip(tensors, tables):
+            for q in range(len(table)):
+                if q != rank and table[q]:
+                    L.fourier_b200_peer_close(table[q])
+            L.fourier_b200_peer_free(t.data_ptr())
+
     def exchange(self, src, table, world, rank, rows_loc, cb, twiddle, first=0, count=None):
         """Rows [first, first + count) of this rank's rows_loc x (world * cb) matrix `src` go, transposed, into
         the peers' buffers (table[q]); twiddle = None or (forward, global index of local row 0, N)."""
@@ -234,6 +244,14 @@ class DistributedFft:
             self._bufs, tables = backend.peer_buffers(self.local_samples(), 2, rank, world, group)
             self._tables = {b.data_ptr(): t for b, t in zip(self._bufs, tables)}
             backend.barrier(group)
+
+    def close(self):
+        """Collective, exchange="peer" only: unmaps the peers' buffers and frees this rank's.  The tensors
+        returned by buffers() are dead afterwards.  (Process exit releases everything as well.)"""
+        if self.exchange == "peer" and self._bufs is not None:
+            self.backend.barrier(self.group)          # nobody is still storing into a buffer that goes away
+            self.backend.peer_release(self._bufs, [self._tables[b.data_ptr()] for b in self._bufs], self.rank)
+            self._bufs, self._tables = None, {}
 
     def buffers(self):
         """The two work buffers to pass to transform(): peer-visible memory with exchange="peer"."""

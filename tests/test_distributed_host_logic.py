@@ -67,3 +67,25 @@ def test_single_rank_degenerates_to_local_transposes():
     x = torch.from_numpy(full.copy())
     out = DistributedFft(n1, n2, 0, 1, NumpyBackend()).transform(x, torch.empty_like(x))
     assert np.abs(out.numpy() - np.fft.fft(full)).max() < 1e-11
+
+
+def test_plan_arguments_and_defaults():
+    sys.path.insert(0, ROOT)
+    from fourier_b200.distributed import DistributedFft, NumpyBackend
+    be = NumpyBackend()
+    with pytest.raises(ValueError):
+        DistributedFft(8, 30, 0, 4, be)                       # 30 rows cannot be split over 4 ranks
+    with pytest.raises(ValueError):
+        DistributedFft(8, 32, 0, 1, be, exchange="mpi")
+    plan = DistributedFft(8, 32, 0, 1, be, exchange="peer")    # a single rank has no peers: local path
+    assert plan.exchange == "nccl" and plan.chunks == 8
+    x, scratch = plan.buffers()
+    assert x.numel() == scratch.numel() == 256 and x.data_ptr() != scratch.data_ptr()
+    assert DistributedFft(64, 64, 1, 4, be, chunks=5)._pieces(16) == 4     # largest divisor of the rows <= chunks
+    assert plan.wire_bytes_per_exchange(8) == 0
+    rng = np.random.default_rng(1)
+    full = (rng.standard_normal(256) + 1j * rng.standard_normal(256)).astype(np.complex128)
+    x.copy_(torch.from_numpy(full))
+    out = plan.transform(x, scratch, forward=False)
+    assert np.abs(out.numpy() - np.fft.ifft(full) * 256).max() < 1e-11
+    plan.close()                                               # no-op outside the peer mode
