@@ -78,6 +78,10 @@ __device__ __forceinline__ void tma_load_2d_first(void* dst, const CUtensorMap* 
       ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
       : "memory");
 }
+// brings a box of the tensor into L2 only (no shared-memory destination, no completion signal)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int x, int y) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -160,15 +164,33 @@ template <typename T> struct FusedArgs {
 //           gather; the refill then overlaps stage B and the stores.  Costs no prefetch distance that
 //           matters (a TMA round trip is shorter than stage B + stores) and frees a third of the shared
 //           memory, i.e. room for one more consumer group.
-template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1>
+// BLOCKED_: the intermediate is stored in 8 x 8 blocks [k1 / 8][n2 / 8][k1 % 8][n2 % 8] instead of row-major
+//           A[k1][n2].  A pass-1 tile then writes 256-byte runs (a warp's store = 4 consecutive k1 x 8 columns)
+//           instead of four 64-byte row pieces -- half the LSU wavefronts -- and a pass-2 tile (8 rows k1) is
+//           still one contiguous bulk copy; its threads pick their samples with the block-fast mapping
+//           (tilefft.cuh), under which a warp needs only 8 different stage twiddles (broadcast loads).
+//           Verified by CPU emulation (tools/emulate.cu); NOT yet run or measured on the GPU.
+// DIRECT_:  no shared-memory staging at all: the consumers load their samples from global memory straight into
+//           registers (pass 1: the input, which the producer lane has prefetched into L2 one tile ahead with
+//           cp.async.bulk.prefetch.tensor; pass 2: the L2-resident blocked intermediate, ld.global.cg).  Saves the
+//           TMA write into shared memory (which stalls the LSU pipe cycle for cycle) and the staging read --
+//           about a third of the LSU wavefronts per tile (profiles/r01_lsu_pipe_analysis.txt) -- and leaves room
+//           for one exchange buffer per group (no lock).  Same verification status as BLOCKED_.
+template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool BLOCKED_ = false, bool DIRECT_ = false>
 struct FusedCfg {
   using T = T_;
   static constexpr bool INPLACE = EXB_ == 0;
+  static constexpr bool BLOCKED = BLOCKED_;
+  static constexpr bool DIRECT = DIRECT_;
+  static_assert(!DIRECT_ || (BLOCKED_ && EXB_ == G_), "direct loads: blocked intermediate, one exchange buffer per group");
   static constexpr int R = R_, C = C_, G = G_, EXB = INPLACE ? G_ : EXB_;
   static constexpr long L = (long)R * R, N1 = L, N2 = L, N = N1 * N2;
   template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
   using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
-  using Lay2 = ExLayout<R * C + 1, C, 1>;                          // pass 2: scatter u-fast, gather col-fast
+  // pass 2: scatter u-fast (row stride = 1 mod 16 elements) or block-fast (= 2 mod 16 for 8-byte, odd for
+  // 16-byte elements: conflict-free for lanes = 8 positions x 4 FFTs), gather col-fast
+  using Lay2 = ExLayout<R * C + (BLOCKED_ ? (sizeof(T_) == 4 ? 2 : 1) : 1), C, 1>;
+  static_assert(!BLOCKED_ || (C_ == 8 && R_ % 8 == 0), "the blocked intermediate needs 8-column tiles");
   static constexpr int GT = R * C;                    // threads per group
   static constexpr int CONSUMERS = G * GT;
   static constexpr int AUX = ((G + 1 + 3) / 4) * 128;  // G producer warps + 1 signaller warp, in whole warpgroups
@@ -189,7 +211,7 @@ struct FusedCfg {
   static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (R / 2) * R;
   // per-group buffer: the staged tile, and in the in-place mode also the (slightly larger) exchange
   static constexpr size_t BUF_BYTES =
-      INPLACE ? (((EX_BYTES > TILE_BYTES ? EX_BYTES : TILE_BYTES) + 1023) / 1024) * 1024 : (size_t)TILE_BYTES;
+      DIRECT ? 0 : INPLACE ? (((EX_BYTES > TILE_BYTES ? EX_BYTES : TILE_BYTES) + 1023) / 1024) * 1024 : (size_t)TILE_BYTES;
   static constexpr int TAB_BUFS = INPLACE ? 1 : 2;   // tile tables: own mbarrier pair (in place) or double buffer
   // layout: staging[G] | exchange | twa | tile tables [G][TAB_BUFS][base, step] | control
   static constexpr size_t OFF_EX = (size_t)G * BUF_BYTES;
@@ -228,6 +250,17 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   d.slot = wi.b & (a.ring - 1);               // ring is a power of two
   ctl->desc = d;
   if (wi.pass < 0) { mbar_arrive(&ctl->full); return; }
+  if constexpr (Cfg::DIRECT) {
+    // nothing to stage: the consumers read global memory themselves; only the tile tables of a pass-1 tile travel
+    if (wi.pass == 1) {
+      mbar_arrive_expect_tx(&ctl->full, 2 * Cfg::TAB_BYTES);
+      bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+      bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    } else {
+      mbar_arrive(&ctl->full);
+    }
+    return;
+  }
   // (the group's reads of `dst` are ordered before this refill by the empty-mbarrier wait of the caller)
   if (wi.pass == 1) {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + (Cfg::INPLACE ? 0 : 2 * Cfg::TAB_BYTES));
@@ -270,6 +303,56 @@ __device__ __forceinline__ const unsigned* dep_counter(const WorkItem& wi, const
   return nullptr;
 }
 
+// The arithmetic of one consumer thread between the barriers of the kernel.  __host__ __device__: the kernel
+// below and tools/emulate.cu (CPU, thread by thread) run exactly this code.
+template <class Cfg, bool FWD> struct FusedMath {
+  using T = typename Cfg::T;
+  using V = cpx<T>;
+  using Tile = typename Cfg::template Tile<FWD>;
+  static constexpr int C = Cfg::C, R = Cfg::R;
+  static constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
+  static constexpr int kMap2 = Cfg::BLOCKED ? kMapBF : kMapUF;     // pass-2 mapping up to the exchange
+  static_assert(!Cfg::BLOCKED || Tile::kBlockFastOk, "tile shape does not fit the block-fast mapping");
+
+  // staging -> registers.  Pass 1: staging = [n1][C] (TMA box); pass 2: C contiguous rows, or 8 x 8 blocks.
+  // DIRECT: `stage` is the tile's first sample in global memory: C columns of x (row stride N2, read once), or the
+  // tile's 8 x 8 blocks of the intermediate (rewritten by other SMs during the kernel: L2 only).
+  static FB_HD void load(Tile& f, int pass, int t, const V* stage) {
+    if constexpr (Cfg::DIRECT) {
+      if (pass == 1) f.template load<kMapCF, N2, 1, 1>(t, stage);
+      else f.template load_blocked<kMapBF, 2>(t, stage);
+    } else {
+      if (pass == 1) f.template load<kMapCF, C, 1>(t, stage);
+      else if constexpr (Cfg::BLOCKED) f.template load_blocked<kMapBF>(t, stage);
+      else f.template load<kMapUF, 1, N2>(t, stage);
+    }
+  }
+  static FB_HD void stage_a(Tile& f, int pass, int t, const TwPair<T>* twa) {
+    if (pass == 1) f.template stage_a<kMapCF>(t, twa); else f.template stage_a<kMap2>(t, twa);
+  }
+  static FB_HD void scatter(const Tile& f, int pass, int t, V* exch) {
+    if (pass == 1) f.template scatter<kMapCF, typename Cfg::Lay1>(t, exch);
+    else f.template scatter<kMap2, typename Cfg::Lay2>(t, exch);
+  }
+  static FB_HD void gather(Tile& f, int pass, int t, const V* exch) {
+    if (pass == 1) f.template gather<kMapCF, typename Cfg::Lay1>(t, exch);
+    else f.template gather<kMapCF, typename Cfg::Lay2>(t, exch);
+  }
+  // pass 1: inter-pass twiddle (factored, tables tb = [base | step]) and store into the ring slot `slot_base`
+  static FB_HD void store1(const Tile& f, int t, V* slot_base, int tile, const V* tb) {
+    if constexpr (Cfg::BLOCKED)
+      f.template store_factored<N2, 1, 2, N2 * 8>(t, slot_base + (size_t)tile * 64, tb, tb + C * R);
+    else
+      f.template store_factored<N2, 1, 2>(t, slot_base + (size_t)tile * C, tb, tb + C * R);   // keep in L2
+  }
+  // pass 2: transposed store of the result, X[k1 + N1 * k2], streaming
+  static FB_HD void store2(const Tile& f, int t, V* out_b, int tile, bool do_scale, T scale) {
+    V* dst = out_b + (size_t)tile * C;
+    if (do_scale) f.template store<kMapCF, N1, 1, false, true, 1>(t, dst, nullptr, scale);
+    else f.template store<kMapCF, N1, 1, false, false, 1>(t, dst, nullptr, scale);
+  }
+};
+
 constexpr int kTraceTiles = 64, kTracePhases = 8;
 #define FB_TRACE(phase)                                                                                   \
   do {                                                                                                    \
@@ -292,8 +375,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2, L = Cfg::L;
   constexpr int T1 = Cfg::T1, T2 = Cfg::T2;
   using Tile = typename Cfg::template Tile<FWD>;
-  using Lay1 = typename Cfg::Lay1;
-  using Lay2 = typename Cfg::Lay2;
+  using Math = FusedMath<Cfg, FWD>;
 
   // No integer round-trip on this pointer: the compiler must keep the shared address space, otherwise
   // every staging/exchange access becomes a generic LD/ST (seen in the first profile of this kernel).
@@ -347,6 +429,21 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       for (uint32_t it = 0;; ++it) {
         const WorkItem wi = decode_work((long)w_next, a.batch, a.lag, T1, T2);
         if (wi.pass >= 0) w_next = atomicAdd(queue, 1u);
+        if constexpr (Cfg::DIRECT) {
+          // the item after this one is known a whole tile period before its group starts on it: long enough for
+          // its input tile to travel from HBM to L2
+          const WorkItem nx = decode_work((long)w_next, a.batch, a.lag, T1, T2);
+          if (wi.pass >= 0 && nx.pass == 1) {
+#pragma unroll
+            for (int r0 = 0; r0 < (int)Cfg::L; r0 += Cfg::BOX_ROWS)
+              tma_prefetch_2d(&in_map, nx.tile * C * 2, (int)((long)nx.b * Cfg::N1 + r0));
+          }
+          if (it == 0 && wi.pass == 1) {   // the very first tile has no predecessor to hide behind
+#pragma unroll
+            for (int r0 = 0; r0 < (int)Cfg::L; r0 += Cfg::BOX_ROWS)
+              tma_prefetch_2d(&in_map, wi.tile * C * 2, (int)((long)wi.b * Cfg::N1 + r0));
+          }
+        }
         FB_PTRACE(0);
         unsigned target;
         const unsigned* dep = dep_counter<Cfg>(wi, a, &target);
@@ -426,10 +523,13 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
 
     // ---- staging -> registers; the staging buffer is free again as soon as every thread has its samples ----
     Tile f;
-    if (wi.pass == 1) f.template load<false, C, 1>(t, stage_g);        // staging = [n1][C]
-    else f.template load<true, 1, N2>(t, stage_g);                     // staging = C contiguous rows
+    if constexpr (Cfg::DIRECT)
+      Math::load(f, wi.pass, t, wi.pass == 1 ? a.in + (size_t)wi.b * N + (size_t)wi.tile * C
+                                             : a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);
+    else
+      Math::load(f, wi.pass, t, stage_g);
     if constexpr (!Cfg::INPLACE) mbar_arrive(&ctl->empty);
-    if (wi.pass == 2) {
+    if (!Cfg::DIRECT && wi.pass == 2) {
       // The intermediate rows this tile just consumed are dead: drop them from L2 instead of letting the
       // cache write them back to HBM later (measured: without this ~80% of the intermediate is written
       // back at RING = 8; the slot is completely rewritten before it is read again).
@@ -438,7 +538,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
     }
-    if (wi.pass == 2 && (t & 31) == 0) {
+    if (!Cfg::DIRECT && wi.pass == 2 && (t & 31) == 0) {
       // the last warp of the group to have pulled its samples reports the ring slot as consumed by this
       // tile -- promptly and from the consumer side (a lazy report by the producer could deadlock it
       // against its own dependency wait)
@@ -446,7 +546,12 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     }
     FB_TRACE(2);
 
-    if (wi.pass == 1) f.template stage_a<false>(t, twa); else f.template stage_a<true>(t, twa);
+    Math::stage_a(f, wi.pass, t, twa);
+    if (Cfg::DIRECT && wi.pass == 2 && (t & 31) == 0) {
+      // same report with direct loads: stage A has consumed every register the warp loaded, so its global loads
+      // have completed
+      if (atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
+    }
 
     // ---- exchange through the shared buffer, under the CTA-wide lock -----------------------------------------
     if (kLocked && t == 0) {
@@ -455,10 +560,17 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     }
     FB_TRACE(3);
     group_sync(bar_id, GT);
-    if (wi.pass == 1) f.template scatter<false, Lay1>(t, exch); else f.template scatter<true, Lay2>(t, exch);
+    if (Cfg::DIRECT && wi.pass == 2) {
+      // every warp of the group is past stage A, i.e. all loads of the tile have completed: drop its rows from L2
+      const unsigned char* rows = reinterpret_cast<const unsigned char*>(
+          a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);
+      for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
+    }
+    Math::scatter(f, wi.pass, t, exch);
     FB_TRACE(4);
     group_sync(bar_id, GT);
-    if (wi.pass == 1) f.template gather<false, Lay1>(t, exch); else f.template gather<false, Lay2>(t, exch);
+    Math::gather(f, wi.pass, t, exch);
     if constexpr (Cfg::INPLACE) {
       mbar_arrive(&ctl->empty);   // the buffer may be refilled once every thread has gathered
     } else {
@@ -473,8 +585,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       const V* tb = tab_g + (Cfg::INPLACE ? 0 : (size_t)(k_p1 & 1) * 2 * C * R);
       if constexpr (Cfg::INPLACE) mbar_wait(&ctl->full_tab, k_p1 & 1);
       ++k_p1;
-      V* dst = a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C;
-      f.template store_factored<N2, 1, 2>(t, dst, tb, tb + C * R);       // intermediate: keep in L2
+      Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb);
       if constexpr (Cfg::INPLACE) mbar_arrive(&ctl->empty_tab);
       // report "stores issued"; the last warp of the group hands the tile to the signaller warp
       __syncwarp();
@@ -488,9 +599,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
         st_release_cta_shared(&ctl->stored_seq, k_p1);
       }
     } else {
-      V* dst = a.out + (size_t)wi.b * N + (size_t)wi.tile * C;
-      if (a.do_scale) f.template store<false, N1, 1, false, true, 1>(t, dst, nullptr, a.scale);   // streaming
-      else f.template store<false, N1, 1, false, false, 1>(t, dst, nullptr, a.scale);
+      Math::store2(f, t, a.out + (size_t)wi.b * N, wi.tile, a.do_scale != 0, a.scale);
     }
     FB_TRACE(6);
   }

@@ -17,6 +17,10 @@
 //   "col fast" (CF): lane -> FFT index inside the tile (used when consecutive FFTs are adjacent in
 //                    memory: column tiles of the four-step algorithm)
 //   "u fast"   (UF): lane -> position inside one FFT (used when one FFT is contiguous in memory)
+//   "block fast" (BF): lane -> (position mod 8, FFT index mod 4), for tiles of 8 FFTs stored in 8 x 8 blocks
+//                    [position / 8][FFT][position mod 8] (the blocked intermediate of the persistent kernel):
+//                    a warp reads 256 contiguous bytes and only 8 different stage twiddles (broadcast)
+// The mapping is a template argument MAP of each access: kMapCF = 0 (false), kMapUF = 1 (true), kMapBF = 2.
 //
 // Every member is __host__ __device__: tools/emulate.cu runs the identical code thread by thread on
 // the CPU (there is no GPU in the build container), tests/test_kernel_emulation.py checks it.
@@ -54,6 +58,18 @@ template <int HINT, typename V> FB_HD void st_hint(V* p, const V& v) {
 #endif
 }
 
+// Global load with a cache hint: 0 = default, 1 = streaming (.cs: read once, evict first), 2 = L2 only (.cg:
+// data other SMs rewrite during the kernel must not be served from a stale L1 line).
+template <int HINT, typename V> FB_HD V ld_hint(const V* p) {
+#if defined(__CUDA_ARCH__)
+  if constexpr (HINT == 1) return __ldcs(p);
+  else if constexpr (HINT == 2) return __ldcg(p);
+  else return *p;
+#else
+  return *p;
+#endif
+}
+
 // Two consecutive twiddles, loaded with one 128-bit (f32) / two 128-bit (f64) instructions.
 template <typename T> struct alignas(2 * sizeof(cpx<T>)) TwPair { cpx<T> a, b; };
 
@@ -66,6 +82,8 @@ template <int SJ_, int SP_, int SC_> struct ExLayout {
   static constexpr int SJ = SJ_, SP = SP_, SC = SC_;
   template <int RA, int RB, int C> static constexpr int elems() { return (RB - 1) * SJ + (RA - 1) * SP + (C - 1) * SC + 1; }
 };
+
+constexpr int kMapCF = 0, kMapUF = 1, kMapBF = 2;
 
 template <typename T, int RA_, int RB_, int E_, int C_, bool FWD_>
 struct TileFFT {
@@ -85,21 +103,43 @@ struct TileFFT {
   using V = cpx<T>;
   V v[E];
 
-  template <bool UF> static FB_HD int col_of(int t) { return UF ? t / TP : t % C; }
-  template <bool UF> static FB_HD int u_of(int t) { return UF ? t % TP : t / C; }
+  template <int MAP> static FB_HD int col_of(int t) {
+    if constexpr (MAP == kMapBF) return ((t & 31) >> 3) + 4 * ((t >> 5) & 1);
+    else return MAP == kMapUF ? t / TP : t % C;
+  }
+  template <int MAP> static FB_HD int u_of(int t) {
+    if constexpr (MAP == kMapBF) return ((t >> 6) << 3) + (t & 7);
+    else return MAP == kMapUF ? t % TP : t / C;
+  }
+  // BF covers the tile exactly once iff there are 8 FFTs per tile and 8 positions per pair of warps
+  static constexpr bool kBlockFastOk = C == 8 && TP % 8 == 0 && THREADS % 64 == 0 && THREADS / 64 * 8 == TP;
 
   // global -> registers.  Sample n of FFT `col` lives at base[col*CS + n*NS].
-  template <bool UF, long NS, long CS> FB_HD void load(int t, const V* __restrict__ base) {
+  template <int UF, long NS, long CS, int HINT = 0> FB_HD void load(int t, const V* __restrict__ base) {
     const int col = col_of<UF>(t), u = u_of<UF>(t);
     const V* p = base + (long)col * CS + (long)u * NS;
 #pragma unroll
     for (int a = 0; a < NA; ++a)
 #pragma unroll
-      for (int i = 0; i < RA; ++i) v[a * RA + i] = p[(long)(TP * a + RB * i) * NS];
+      for (int i = 0; i < RA; ++i) {
+        if constexpr (HINT == 0) v[a * RA + i] = p[(long)(TP * a + RB * i) * NS];
+        else v[a * RA + i] = ld_hint<HINT>(p + (long)(TP * a + RB * i) * NS);
+      }
+  }
+
+  // Same for a tile of C = 8 FFTs stored in 8 x 8 blocks: sample n of FFT `col` at (n / 8) * 64 + col * 8 + n % 8.
+  template <int MAP, int HINT = 0> FB_HD void load_blocked(int t, const V* __restrict__ base) {
+    static_assert(C == 8 && RB % 8 == 0 && TP % 8 == 0, "blocked tiles hold 8 FFTs");
+    const int col = col_of<MAP>(t), u = u_of<MAP>(t);
+    const V* p = base + (u >> 3) * 64 + col * 8 + (u & 7);
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int i = 0; i < RA; ++i) v[a * RA + i] = ld_hint<HINT>(p + (TP * a + RB * i) * 8);   // (.. / 8) blocks of 64
   }
 
   // DFT_RA over i for each owned j, then the stage twiddle w_L^{j*p} (skipped for p == 0).
-  template <bool UF> FB_HD void stage_a(int t, const TwPair<T>* __restrict__ twa) {
+  template <int UF> FB_HD void stage_a(int t, const TwPair<T>* __restrict__ twa) {
     const int u = u_of<UF>(t);
     static_for<0, NA>([&](auto A) FB_LAMBDA {
       constexpr int a = decltype(A)::value;
@@ -115,7 +155,7 @@ struct TileFFT {
   }
 
   // registers -> shared (layout LAY)
-  template <bool UF, class LAY> FB_HD void scatter(int t, V* smem) const {
+  template <int UF, class LAY> FB_HD void scatter(int t, V* smem) const {
     constexpr int SJ = LAY::SJ, SP = LAY::SP, SC = LAY::SC;
     const int col = col_of<UF>(t), u = u_of<UF>(t);
     static_for<0, NA>([&](auto A) FB_LAMBDA {
@@ -129,7 +169,7 @@ struct TileFFT {
   }
 
   // shared -> registers for stage B: thread owns p = u + TP*c, reads all j
-  template <bool UF, class LAY> FB_HD void gather(int t, const V* smem) {
+  template <int UF, class LAY> FB_HD void gather(int t, const V* smem) {
     constexpr int SJ = LAY::SJ, SP = LAY::SP, SC = LAY::SC;
     const int col = col_of<UF>(t), u = u_of<UF>(t);
 #pragma unroll
@@ -150,7 +190,7 @@ struct TileFFT {
   // registers -> global.  Output k = p + RA*r of FFT `col` goes to base[col*CS + k*KS], optionally
   // multiplied by the inter-pass twiddle tw2[col*CS + k*KS] (same layout as the destination) and by
   // a real scale factor.
-  template <bool UF, long KS, long CS, bool TW2, bool SCALE, int HINT = 0>
+  template <int UF, long KS, long CS, bool TW2, bool SCALE, int HINT = 0>
   FB_HD void store(int t, V* __restrict__ base, const V* __restrict__ tw2, T scale) const {
     const int col = col_of<UF>(t), u = u_of<UF>(t);
     static_for<0, NB>([&](auto Cc) FB_LAMBDA {
@@ -196,18 +236,23 @@ struct TileFFT {
   //   w_N^{n2*(p + RA*r)} = base[n2][p] * step[n2][r],  base = w_N^{n2*p},  step = w_N^{RA*n2*r}.
   // sbase is laid out [col][p], sstep [r][col] (lanes that differ in col read adjacent words, lanes that
   // differ in p broadcast).  Costs one extra complex multiply per sample and no global-memory load.
-  template <long KS, long CS, int HINT>
+  // BLOCK_ROW > 0: the destination is the blocked intermediate [k / 8][tile][k % 8][col] with BLOCK_ROW
+  // elements per k-block row (= 64 * tiles per row) and `base` pointing at the tile's block of row 0: the 4
+  // consecutive k of a warp and its 8 columns form one 256-byte run.
+  template <long KS, long CS, int HINT, long BLOCK_ROW = 0>
   FB_HD void store_factored(int t, V* __restrict__ base, const V* sbase, const V* sstep) const {
     const int col = col_of<false>(t), u = u_of<false>(t);
+    static_assert(BLOCK_ROW == 0 || (C == 8 && RA % 8 == 0), "blocked intermediate: 8 columns per tile");
     static_for<0, NB>([&](auto Cc) FB_LAMBDA {
       constexpr int c = decltype(Cc)::value;
       const int p = u + TP * c;
-      const long off = (long)col * CS + (long)p * KS;
+      const long off = BLOCK_ROW ? (long)(p >> 3) * BLOCK_ROW + (p & 7) * 8 + col : (long)col * CS + (long)p * KS;
       const V wb = sbase[col * RA + p];
       static_for<0, RB>([&](auto Rr) FB_LAMBDA {
         constexpr int r = decltype(Rr)::value;
         const V w = cmul(wb, sstep[r * C + col]);
-        st_hint<HINT>(&base[off + (long)(RA * r) * KS], ctw<FWD>(v[c * RB + bitrev(r, ilog2(RB))], w));
+        constexpr long step = BLOCK_ROW ? (long)(RA * r / 8) * BLOCK_ROW : (long)(RA * r) * KS;
+        st_hint<HINT>(&base[off + step], ctw<FWD>(v[c * RB + bitrev(r, ilog2(RB))], w));
       });
     });
   }

@@ -113,6 +113,10 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
       // exchange in place in the staging buffer: two groups / three groups
       case 3: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 0>>::ops(8, 4);
       case 4: return FusedImpl<fused::FusedCfg<float, 32, 8, 3, 8, 0>>::ops(16, 6);
+      // default shape with the intermediate in 8 x 8 blocks (CPU-emulated only so far, see FusedCfg)
+      case 5: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1, true>>::ops(8, 4);
+      // blocked intermediate + direct global->register loads (no staging), one exchange buffer per group
+      case 6: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 2, true, true>>::ops(8, 4);
       default: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
     }
   }
@@ -124,6 +128,8 @@ template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
       case 1: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
       case 3: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 0>>::ops(64, 32);
       case 4: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 0>>::ops(128, 48);
+      case 5: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3, true>>::ops(64, 32);
+      case 6: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true, true>>::ops(64, 32);
       default: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
     }
   }
@@ -162,18 +168,8 @@ cudaError_t Plan<T>::init_twopass() {
     if (f && f->n1 == n1_ && f->n2 == n2_ && f->prepare() == cudaSuccess) {
       // factored inter-pass twiddles, contiguous per pass-1 tile of `tile_c` columns:
       //   tbase[tile][col][p] = w_N^{n2*p},  tstep[tile][r][col] = w_N^{R*n2*r},  n2 = tile*tile_c + col
-      const int rr = f->ra, cc = f->tile_c;
-      std::vector<cpx<T>> tb((size_t)n2_ * rr), ts((size_t)n2_ * rr);
-      for (size_t c2 = 0; c2 < n2_; ++c2) {
-        const size_t tile = c2 / cc, col = c2 % cc;
-        for (int q = 0; q < rr; ++q) {
-          double re, im;
-          host_twiddle(c2 * (size_t)q, n_, &re, &im);
-          tb[(tile * cc + col) * rr + q] = mk<T>((T)re, (T)im);
-          host_twiddle((size_t)rr * c2 * (size_t)q, n_, &re, &im);
-          ts[(tile * rr + q) * cc + col] = mk<T>((T)re, (T)im);
-        }
-      }
+      std::vector<cpx<T>> tb, ts;
+      make_factored_twiddles<T>(n_, n2_, f->ra, f->tile_c, tb, ts);
       FB_CHECK((upload_vec<T, cpx<T>>(tbase_, tb)));
       FB_CHECK((upload_vec<T, cpx<T>>(tstep_, ts)));
       fused_ops_ = f;

@@ -5,6 +5,7 @@
 // It also reports shared-memory bank conflicts of the exchange (64-bit/128-bit access model).
 // Build: nvcc -std=c++17 -O1 --expt-relaxed-constexpr -I fourier_b200/csrc tools/emulate.cu \
 //             fourier_b200/csrc/plan.cu ... (host only, never run on the device)
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -62,7 +63,7 @@ static void run_body(const typename Body::Args& a, long blocks) {
 }
 
 // Bank-conflict report for the exchange of a tile: scatter with mapping UF_A, gather with col-fast.
-template <class Tile, class LAY, bool UF_A, bool UF_B = false>
+template <class Tile, class LAY, int UF_A, int UF_B = 0>
 static void report_conflicts(const char* name) {
   using V = typename Tile::V;
   constexpr int B = (int)sizeof(V);
@@ -260,6 +261,105 @@ static int check_bluestein(const char* name, long n, double tol) {
   return bad;
 }
 
+// ---- persistent kernel: the consumer arithmetic (fused::FusedMath) with the producer / TMA side replaced by
+// plain copies: staging = what the TMA box (pass 1) or the bulk copy (pass 2) would deliver --------------------------
+template <class Cfg>
+static int check_fused(const char* name, double tol) {
+  using T = typename Cfg::T;
+  using V = cpx<T>;
+  constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
+  constexpr int C = Cfg::C, R = Cfg::R, GT = Cfg::GT;
+  printf("%s: persistent-kernel arithmetic, N=%ld, %s intermediate%s\n", name, N, Cfg::BLOCKED ? "blocked" : "row-major",
+         Cfg::DIRECT ? ", direct loads" : "");
+  report_conflicts<typename Cfg::template Tile<true>, typename Cfg::Lay1, kMapCF>("pass 1");
+  report_conflicts<typename Cfg::template Tile<true>, typename Cfg::Lay2, fused::FusedMath<Cfg, true>::kMap2>("pass 2");
+  {  // staging reads of pass 2 (the other staging / table reads are contiguous by construction)
+    using Tile = typename Cfg::template Tile<true>;
+    int worst = 1;
+    for (int warp = 0; warp < GT / 32; ++warp)
+      for (int i = 0; i < Tile::RA; ++i) {
+        std::vector<long> idx;
+        for (int l = 0; l < 32; ++l) {
+          const int t = warp * 32 + l;
+          constexpr int M = fused::FusedMath<Cfg, true>::kMap2;
+          const long u = Tile::template u_of<M>(t), col = Tile::template col_of<M>(t), n = u + (long)Tile::RB * i;
+          idx.push_back(Cfg::BLOCKED ? (n / 8) * 64 + col * 8 + n % 8 : col * N2 + n);
+        }
+        worst = std::max(worst, conflict_degree<(int)sizeof(V)>(idx));
+      }
+    printf("  pass 2 staging reads: conflicts x%d %s\n", worst, worst == 1 ? "" : "FAIL");
+    if (worst != 1) return 1;
+  }
+  {  // LSU cost model of the two accesses the blocked layout changes: 128-byte lines touched by one warp-wide
+     // pass-1 store, and different stage twiddles one warp loads in pass 2 (identical addresses broadcast)
+    using Tile = typename Cfg::template Tile<true>;
+    constexpr int M = fused::FusedMath<Cfg, true>::kMap2;
+    long lines = 0, twiddles = 0;
+    for (int warp = 0; warp < GT / 32; ++warp) {
+      std::vector<long> seen_l, seen_t;
+      for (int l = 0; l < 32; ++l) {
+        const int t = warp * 32 + l;
+        const long col = Tile::template col_of<kMapCF>(t), p = Tile::template u_of<kMapCF>(t);
+        const long e = Cfg::BLOCKED ? (p >> 3) * (N2 * 8) + (p & 7) * 8 + col : col + p * N2;   // output r = 0
+        const long line = e * (long)sizeof(V) / 128, tw = Tile::template u_of<M>(t);
+        if (std::find(seen_l.begin(), seen_l.end(), line) == seen_l.end()) seen_l.push_back(line);
+        if (std::find(seen_t.begin(), seen_t.end(), tw) == seen_t.end()) seen_t.push_back(tw);
+      }
+      lines += (long)seen_l.size();
+      twiddles += (long)seen_t.size();
+    }
+    printf("  per warp: %.1f lines of 128 B per pass-1 store instruction (%d B stored), %.1f different pass-2 stage twiddles\n",
+           (double)lines / (GT / 32), 32 * (int)sizeof(V), (double)twiddles / (GT / 32));
+  }
+  auto twa = make_twa<T>(R, R);
+  std::vector<V> tbase, tstep;
+  make_factored_twiddles<T>((size_t)N, (size_t)N2, R, C, tbase, tstep);
+  int bad = 0;
+  for (int fwd = 1; fwd >= 0; --fwd) {
+    std::vector<V> x(N), scratch(N), out(N), staging((size_t)C * Cfg::L), tab(2 * (size_t)C * R);
+    std::vector<V> exch(Cfg::EX_ELEMS);
+    fill<T>(x, 41 + fwd);
+    const T scale = (T)0.5;
+    auto run_tile = [&](auto fwd_tag, int pass, int tile) {
+      constexpr bool FWD = decltype(fwd_tag)::value;
+      using Math = fused::FusedMath<Cfg, FWD>;
+      std::vector<typename Math::Tile> thr(GT);
+      // direct mode: the threads read global memory themselves (same pointers as the kernel computes)
+      const V* src = !Cfg::DIRECT ? staging.data() : pass == 1 ? x.data() + (size_t)tile * C : scratch.data() + (size_t)tile * C * N2;
+      for (int t = 0; t < GT; ++t) { Math::load(thr[t], pass, t, src); Math::stage_a(thr[t], pass, t, twa.data()); }
+      for (int t = 0; t < GT; ++t) Math::scatter(thr[t], pass, t, exch.data());
+      for (int t = 0; t < GT; ++t) {
+        Math::gather(thr[t], pass, t, exch.data());
+        thr[t].stage_b();
+        if (pass == 1) Math::store1(thr[t], t, scratch.data(), tile, tab.data());
+        else Math::store2(thr[t], t, out.data(), tile, true, scale);
+      }
+    };
+    for (int tile = 0; tile < Cfg::T1; ++tile) {        // pass 1: TMA box = rows n1, columns tile*C .. +C
+      for (long r = 0; r < N1; ++r)
+        for (int c = 0; c < C; ++c) staging[r * C + c] = x[r * N2 + (long)tile * C + c];
+      for (int i = 0; i < C * R; ++i) { tab[i] = tbase[(size_t)tile * C * R + i]; tab[C * R + i] = tstep[(size_t)tile * C * R + i]; }
+      if (fwd) run_tile(std::true_type{}, 1, tile); else run_tile(std::false_type{}, 1, tile);
+    }
+    for (int tile = 0; tile < Cfg::T2; ++tile) {        // pass 2: bulk copy of C*N2 contiguous samples
+      for (long i = 0; i < (long)C * N2; ++i) staging[i] = scratch[(size_t)tile * C * N2 + i];
+      if (fwd) run_tile(std::true_type{}, 2, tile); else run_tile(std::false_type{}, 2, tile);
+    }
+    std::vector<double> re(N), im(N);
+    for (long i = 0; i < N; ++i) { re[i] = x[i].x; im[i] = x[i].y; }
+    host_fft_pow2(re, im, !fwd);
+    double maxref = 0, maxerr = 0;
+    for (long i = 0; i < N; ++i) {
+      maxref = std::max(maxref, std::hypot(re[i], im[i]) * 0.5);
+      maxerr = std::max(maxerr, std::hypot(out[i].x - 0.5 * re[i], out[i].y - 0.5 * im[i]));
+    }
+    printf("  %s: max rel err vs f64 FFT %.3e (tol %.1e) %s\n", fwd ? "forward" : "inverse", maxerr / maxref, tol,
+           maxerr / maxref < tol ? "OK" : "FAIL");
+    bad += !(maxerr / maxref < tol);
+  }
+  return bad;
+}
+
 // ---- work queue of the fused kernel: order and dependency properties ---------------------------------------------
 static int check_queue() {
   int bad = 0;
@@ -334,6 +434,12 @@ int main() {
   bad += check_bluestein<float, 8, 8>("bluestein f32", 37, 3e-6);
   bad += check_bluestein<double, 16, 8>("bluestein f64", 191, 1e-13);
   bad += check_bluestein<double, 8, 8>("bluestein f64", 61, 1e-13);
+  bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 8, 1>>("fused f32 2^20", 2e-6);
+  bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 8, 1, true>>("fused f32 2^20", 2e-6);
+  bad += check_fused<fused::FusedCfg<double, 16, 8, 3, 4, 3>>("fused f64 2^16", 5e-15);
+  bad += check_fused<fused::FusedCfg<double, 16, 8, 3, 4, 3, true>>("fused f64 2^16", 5e-15);
+  bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 8, 2, true, true>>("fused f32 2^20", 2e-6);
+  bad += check_fused<fused::FusedCfg<double, 16, 8, 4, 4, 4, true, true>>("fused f64 2^16", 5e-15);
   bad += check_queue();
   printf(bad ? "EMULATION FAILED (%d)\n" : "EMULATION OK\n", bad);
   return bad ? 1 : 0;
