@@ -14,6 +14,7 @@
 // (q = me+1, me+2, ... per consecutive block) so that every rank feeds all its peers at the same rate and no
 // receiver's ingress is oversubscribed.  Ordering between ranks (all tiles have landed / the source may be
 // overwritten) is a stream-ordered barrier issued by the caller after the kernel.
+#include <cstdlib>
 #include <cstring>
 
 #include "plan.h"
@@ -23,13 +24,18 @@ namespace {
 
 struct PeerPtrs { void* p[kMaxPeers]; };
 
-template <typename T, int TW>
+// PERSIST: a fixed number of blocks walks over the tiles (grid-stride), so that the kernel occupies only part of
+// the GPU and kernels on other streams (the row FFTs of the next block of rows) run beside it; enough blocks must
+// stay in flight to cover the NVLink latency (~2 MB of tiles).  Experiment knob, see launch_exchange.
+template <typename T, int TW, bool PERSIST>
 __global__ void __launch_bounds__(256)
 exchange_kernel(const cpx<T>* __restrict__ in, PeerPtrs outs, int nranks, int me, size_t rows, size_t cb, size_t ld,
-                size_t out_ld, size_t out_off, unsigned tiles_c, unsigned long long row0, unsigned long long n_total) {
+                size_t out_ld, size_t out_off, unsigned tiles_c, unsigned long long row0, unsigned long long n_total,
+                unsigned total_tiles) {
   using V = cpx<T>;
   __shared__ V tile[32][33];
-  const unsigned id = blockIdx.x;
+  for (unsigned id = blockIdx.x; PERSIST ? id < total_tiles : id == blockIdx.x; id += gridDim.x) {
+  if (PERSIST && id != blockIdx.x) __syncthreads();   // the previous tile has left shared memory
   const int q = (me + 1 + (int)(id % (unsigned)nranks)) % nranks;
   const unsigned t = id / (unsigned)nranks;
   const size_t c0 = (size_t)(t % tiles_c) * 32, r0 = (size_t)(t / tiles_c) * 32;
@@ -63,6 +69,12 @@ exchange_kernel(const cpx<T>* __restrict__ in, PeerPtrs outs, int nranks, int me
   __syncthreads();
   for (int i = ty; i < 32; i += 8)
     if (c0 + i < cb && r0 + tx < rows) dst[(c0 + i) * out_ld + r0 + tx] = tile[tx][i];
+  }
+}
+
+int env_blocks() {
+  const char* e = std::getenv("FOURIER_B200_EXCHANGE_BLOCKS");
+  return e ? atoi(e) : 0;
 }
 
 }  // namespace
@@ -84,13 +96,22 @@ cudaError_t launch_exchange(const cpx<T>* in, void* const* outs, int nranks, int
   }
   PeerPtrs p;
   for (int i = 0; i < kMaxPeers; ++i) p.p[i] = i < nranks ? outs[i] : nullptr;
-  const unsigned grid = (unsigned)(tiles_c * tiles_r * (size_t)nranks);
-  if (twiddle == 0)
-    exchange_kernel<T, 0><<<grid, 256, 0, s>>>(in, p, nranks, me, rows, cb, ld, out_ld, out_off, (unsigned)tiles_c, row0, n_total);
-  else if (twiddle == 1)
-    exchange_kernel<T, 1><<<grid, 256, 0, s>>>(in, p, nranks, me, rows, cb, ld, out_ld, out_off, (unsigned)tiles_c, row0, n_total);
-  else
-    exchange_kernel<T, 2><<<grid, 256, 0, s>>>(in, p, nranks, me, rows, cb, ld, out_ld, out_off, (unsigned)tiles_c, row0, n_total);
+  const unsigned total = (unsigned)(tiles_c * tiles_r * (size_t)nranks);
+  // FOURIER_B200_EXCHANGE_BLOCKS=n (experiment, not yet measured): n persistent blocks instead of one block per tile
+  const int limit = env_blocks();
+#define FB_EXCHANGE_LAUNCH(TW)                                                                                      \
+  do {                                                                                                               \
+    if (limit > 0 && (unsigned)limit < total)                                                                        \
+      exchange_kernel<T, TW, true><<<(unsigned)limit, 256, 0, s>>>(in, p, nranks, me, rows, cb, ld, out_ld, out_off, \
+                                                                   (unsigned)tiles_c, row0, n_total, total);         \
+    else                                                                                                             \
+      exchange_kernel<T, TW, false><<<total, 256, 0, s>>>(in, p, nranks, me, rows, cb, ld, out_ld, out_off,          \
+                                                          (unsigned)tiles_c, row0, n_total, total);                  \
+  } while (0)
+  if (twiddle == 0) FB_EXCHANGE_LAUNCH(0);
+  else if (twiddle == 1) FB_EXCHANGE_LAUNCH(1);
+  else FB_EXCHANGE_LAUNCH(2);
+#undef FB_EXCHANGE_LAUNCH
   return cudaGetLastError();
 }
 template cudaError_t launch_exchange<float>(const cpx<float>*, void* const*, int, int, size_t, size_t, size_t, size_t,
