@@ -170,19 +170,20 @@ template <typename T> struct FusedArgs {
 //           still one contiguous bulk copy; its threads pick their samples with the block-fast mapping
 //           (tilefft.cuh), under which a warp needs only 8 different stage twiddles (broadcast loads).
 //           Verified by CPU emulation (tools/emulate.cu); NOT yet run or measured on the GPU.
-// DIRECT_:  no shared-memory staging at all: the consumers load their samples from global memory straight into
+// DIRECT_:  1 = no shared-memory staging at all: the consumers load their samples from global memory straight into
 //           registers (pass 1: the input, which the producer lane has prefetched into L2 one tile ahead with
 //           cp.async.bulk.prefetch.tensor; pass 2: the L2-resident blocked intermediate, ld.global.cg).  Saves the
 //           TMA write into shared memory (which stalls the LSU pipe cycle for cycle) and the staging read --
 //           about a third of the LSU wavefronts per tile (profiles/r01_lsu_pipe_analysis.txt) -- and leaves room
-//           for one exchange buffer per group (no lock).  Same verification status as BLOCKED_.
-template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool BLOCKED_ = false, bool DIRECT_ = false>
+//           for one exchange buffer per group (no lock).  2 = only pass 2 loads directly (its source is always an
+//           L2 hit); pass 1 keeps the TMA staging.  Same verification status as BLOCKED_.
+template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool BLOCKED_ = false, int DIRECT_ = 0>
 struct FusedCfg {
   using T = T_;
   static constexpr bool INPLACE = EXB_ == 0;
   static constexpr bool BLOCKED = BLOCKED_;
-  static constexpr bool DIRECT = DIRECT_;
-  static_assert(!DIRECT_ || (BLOCKED_ && EXB_ == G_), "direct loads: blocked intermediate, one exchange buffer per group");
+  static constexpr bool DIRECT_P1 = DIRECT_ == 1, DIRECT_P2 = DIRECT_ != 0;
+  static_assert(DIRECT_ == 0 || (BLOCKED_ && EXB_ != 0), "direct loads: blocked intermediate, separate exchange buffers");
   static constexpr int R = R_, C = C_, G = G_, EXB = INPLACE ? G_ : EXB_;
   static constexpr long L = (long)R * R, N1 = L, N2 = L, N = N1 * N2;
   template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
@@ -211,7 +212,7 @@ struct FusedCfg {
   static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (R / 2) * R;
   // per-group buffer: the staged tile, and in the in-place mode also the (slightly larger) exchange
   static constexpr size_t BUF_BYTES =
-      DIRECT ? 0 : INPLACE ? (((EX_BYTES > TILE_BYTES ? EX_BYTES : TILE_BYTES) + 1023) / 1024) * 1024 : (size_t)TILE_BYTES;
+      DIRECT_P1 ? 0 : INPLACE ? (((EX_BYTES > TILE_BYTES ? EX_BYTES : TILE_BYTES) + 1023) / 1024) * 1024 : (size_t)TILE_BYTES;
   static constexpr int TAB_BUFS = INPLACE ? 1 : 2;   // tile tables: own mbarrier pair (in place) or double buffer
   // layout: staging[G] | exchange | twa | tile tables [G][TAB_BUFS][base, step] | control
   static constexpr size_t OFF_EX = (size_t)G * BUF_BYTES;
@@ -250,17 +251,15 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   d.slot = wi.b & (a.ring - 1);               // ring is a power of two
   ctl->desc = d;
   if (wi.pass < 0) { mbar_arrive(&ctl->full); return; }
-  if constexpr (Cfg::DIRECT) {
-    // nothing to stage: the consumers read global memory themselves; only the tile tables of a pass-1 tile travel
-    if (wi.pass == 1) {
-      mbar_arrive_expect_tx(&ctl->full, 2 * Cfg::TAB_BYTES);
-      bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
-      bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
-    } else {
-      mbar_arrive(&ctl->full);
-    }
+  // direct loads: nothing to stage, the consumers read global memory themselves; only the tile tables of a
+  // pass-1 tile travel
+  if (Cfg::DIRECT_P1 && wi.pass == 1) {
+    mbar_arrive_expect_tx(&ctl->full, 2 * Cfg::TAB_BYTES);
+    bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
     return;
   }
+  if (Cfg::DIRECT_P2 && wi.pass == 2) { mbar_arrive(&ctl->full); return; }
   // (the group's reads of `dst` are ordered before this refill by the empty-mbarrier wait of the caller)
   if (wi.pass == 1) {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + (Cfg::INPLACE ? 0 : 2 * Cfg::TAB_BYTES));
@@ -318,11 +317,11 @@ template <class Cfg, bool FWD> struct FusedMath {
   // DIRECT: `stage` is the tile's first sample in global memory: C columns of x (row stride N2, read once), or the
   // tile's 8 x 8 blocks of the intermediate (rewritten by other SMs during the kernel: L2 only).
   static FB_HD void load(Tile& f, int pass, int t, const V* stage) {
-    if constexpr (Cfg::DIRECT) {
-      if (pass == 1) f.template load<kMapCF, N2, 1, 1>(t, stage);
-      else f.template load_blocked<kMapBF, 2>(t, stage);
+    if (pass == 1) {
+      if constexpr (Cfg::DIRECT_P1) f.template load<kMapCF, N2, 1, 1>(t, stage);
+      else f.template load<kMapCF, C, 1>(t, stage);
     } else {
-      if (pass == 1) f.template load<kMapCF, C, 1>(t, stage);
+      if constexpr (Cfg::DIRECT_P2) f.template load_blocked<kMapBF, 2>(t, stage);
       else if constexpr (Cfg::BLOCKED) f.template load_blocked<kMapBF>(t, stage);
       else f.template load<kMapUF, 1, N2>(t, stage);
     }
@@ -429,7 +428,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       for (uint32_t it = 0;; ++it) {
         const WorkItem wi = decode_work((long)w_next, a.batch, a.lag, T1, T2);
         if (wi.pass >= 0) w_next = atomicAdd(queue, 1u);
-        if constexpr (Cfg::DIRECT) {
+        if constexpr (Cfg::DIRECT_P1) {
           // the item after this one is known a whole tile period before its group starts on it: long enough for
           // its input tile to travel from HBM to L2
           const WorkItem nx = decode_work((long)w_next, a.batch, a.lag, T1, T2);
@@ -523,13 +522,11 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
 
     // ---- staging -> registers; the staging buffer is free again as soon as every thread has its samples ----
     Tile f;
-    if constexpr (Cfg::DIRECT)
-      Math::load(f, wi.pass, t, wi.pass == 1 ? a.in + (size_t)wi.b * N + (size_t)wi.tile * C
-                                             : a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);
-    else
-      Math::load(f, wi.pass, t, stage_g);
+    if (Cfg::DIRECT_P1 && wi.pass == 1) Math::load(f, 1, t, a.in + (size_t)wi.b * N + (size_t)wi.tile * C);
+    else if (Cfg::DIRECT_P2 && wi.pass == 2) Math::load(f, 2, t, a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);
+    else Math::load(f, wi.pass, t, stage_g);
     if constexpr (!Cfg::INPLACE) mbar_arrive(&ctl->empty);
-    if (!Cfg::DIRECT && wi.pass == 2) {
+    if (!Cfg::DIRECT_P2 && wi.pass == 2) {
       // The intermediate rows this tile just consumed are dead: drop them from L2 instead of letting the
       // cache write them back to HBM later (measured: without this ~80% of the intermediate is written
       // back at RING = 8; the slot is completely rewritten before it is read again).
@@ -538,7 +535,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
     }
-    if (!Cfg::DIRECT && wi.pass == 2 && (t & 31) == 0) {
+    if (!Cfg::DIRECT_P2 && wi.pass == 2 && (t & 31) == 0) {
       // the last warp of the group to have pulled its samples reports the ring slot as consumed by this
       // tile -- promptly and from the consumer side (a lazy report by the producer could deadlock it
       // against its own dependency wait)
@@ -547,7 +544,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     FB_TRACE(2);
 
     Math::stage_a(f, wi.pass, t, twa);
-    if (Cfg::DIRECT && wi.pass == 2 && (t & 31) == 0) {
+    if (Cfg::DIRECT_P2 && wi.pass == 2 && (t & 31) == 0) {
       // same report with direct loads: stage A has consumed every register the warp loaded, so its global loads
       // have completed
       if (atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
@@ -560,7 +557,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     }
     FB_TRACE(3);
     group_sync(bar_id, GT);
-    if (Cfg::DIRECT && wi.pass == 2) {
+    if (Cfg::DIRECT_P2 && wi.pass == 2) {
       // every warp of the group is past stage A, i.e. all loads of the tile have completed: drop its rows from L2
       const unsigned char* rows = reinterpret_cast<const unsigned char*>(
           a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);

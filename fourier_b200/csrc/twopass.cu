@@ -116,7 +116,9 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
       // default shape with the intermediate in 8 x 8 blocks (CPU-emulated only so far, see FusedCfg)
       case 5: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1, true>>::ops(8, 4);
       // blocked intermediate + direct global->register loads (no staging), one exchange buffer per group
-      case 6: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 2, true, true>>::ops(8, 4);
+      case 6: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 2, true, 1>>::ops(8, 4);
+      // blocked intermediate + direct loads in pass 2 only (pass 1 keeps the TMA staging, shared exchange buffer)
+      case 7: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1, true, 2>>::ops(8, 4);
       default: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
     }
   }
@@ -129,7 +131,8 @@ template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
       case 3: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 0>>::ops(64, 32);
       case 4: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 0>>::ops(128, 48);
       case 5: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3, true>>::ops(64, 32);
-      case 6: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true, true>>::ops(64, 32);
+      case 6: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true, 1>>::ops(64, 32);
+      case 7: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3, true, 2>>::ops(64, 32);
       default: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
     }
   }
