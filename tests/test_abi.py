@@ -117,3 +117,19 @@ def test_product_never_imports_the_oracle():
                 assert not bad.search(text), f
     out = subprocess.run(["readelf", "-d", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     assert "oracle" not in out
+
+
+@pytest.mark.skipif(shutil.which("cmake") is None or (shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc")),
+                    reason="cmake / nvcc not available")
+def test_cmake_package_configures(tmp_path):
+    """CMakeLists.txt (the packaging that mirrors fourier-ffi/CMakeLists.txt: shared + static `fourier`, the four
+    C / C++ test programs, find_package config) must at least configure; the full build takes minutes and is not
+    part of the CPU suite."""
+    env = dict(os.environ)
+    env.setdefault("CUDACXX", shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc")
+    r = subprocess.run(["cmake", "-S", ROOT, "-B", str(tmp_path / "b"), "-DCMAKE_BUILD_TYPE=Release"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    targets = subprocess.run(["cmake", "--build", str(tmp_path / "b"), "--target", "help"], capture_output=True, text=True).stdout
+    for t in ("fourier_shared", "fourier_static", "test_c_static", "test_c_shared", "test_cpp_static", "test_cpp_shared"):
+        assert t in targets, targets
