@@ -171,7 +171,7 @@ template <typename T> struct FusedArgs {
 //           (tilefft.cuh), under which a warp needs only 8 different stage twiddles (broadcast loads).
 //           Verified by CPU emulation (tools/emulate.cu); NOT yet run or measured on the GPU.
 // DIRECT_:  1 = no shared-memory staging at all: the consumers load their samples from global memory straight into
-//           registers (pass 1: the input, which the producer lane has prefetched into L2 one tile ahead with
+//           registers (pass 1: the input, which the producer lane has prefetched into L2 one tile period ahead with
 //           cp.async.bulk.prefetch.tensor; pass 2: the L2-resident blocked intermediate, ld.global.cg).  Saves the
 //           TMA write into shared memory (which stalls the LSU pipe cycle for cycle) and the staging read --
 //           about a third of the LSU wavefronts per tile (profiles/r01_lsu_pipe_analysis.txt) -- and leaves room
@@ -428,27 +428,22 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       for (uint32_t it = 0;; ++it) {
         const WorkItem wi = decode_work((long)w_next, a.batch, a.lag, T1, T2);
         if (wi.pass >= 0) w_next = atomicAdd(queue, 1u);
-        if constexpr (Cfg::DIRECT_P1) {
-          // the item after this one is known a whole tile period before its group starts on it: long enough for
-          // its input tile to travel from HBM to L2
-          const WorkItem nx = decode_work((long)w_next, a.batch, a.lag, T1, T2);
-          if (wi.pass >= 0 && nx.pass == 1) {
-#pragma unroll
-            for (int r0 = 0; r0 < (int)Cfg::L; r0 += Cfg::BOX_ROWS)
-              tma_prefetch_2d(&in_map, nx.tile * C * 2, (int)((long)nx.b * Cfg::N1 + r0));
-          }
-          if (it == 0 && wi.pass == 1) {   // the very first tile has no predecessor to hide behind
-#pragma unroll
-            for (int r0 = 0; r0 < (int)Cfg::L; r0 += Cfg::BOX_ROWS)
-              tma_prefetch_2d(&in_map, wi.tile * C * 2, (int)((long)wi.b * Cfg::N1 + r0));
-          }
-        }
         FB_PTRACE(0);
         unsigned target;
         const unsigned* dep = dep_counter<Cfg>(wi, a, &target);
         if (dep) { spin_until_ge(dep, target); fence_proxy_async(); }
         FB_PTRACE(1);
         if (it > 0) mbar_wait(&ctl->empty, (it - 1) & 1);
+        if constexpr (Cfg::DIRECT_P1) {
+          // The group has just started on the previous item, so it will ask for this tile one tile period from now
+          // (~5 us): long enough for HBM -> L2, short enough that the prefetched tiles of all groups (148 x G x 64 KB)
+          // do not crowd the intermediate out of L2.
+          if (wi.pass == 1) {
+#pragma unroll
+            for (int r0 = 0; r0 < (int)Cfg::L; r0 += Cfg::BOX_ROWS)
+              tma_prefetch_2d(&in_map, wi.tile * C * 2, (int)((long)wi.b * Cfg::N1 + r0));
+          }
+        }
         FB_PTRACE(2);
         if constexpr (Cfg::INPLACE) {
           // the buffer was last written by the group's own (generic-proxy) exchange stores
