@@ -2,6 +2,8 @@
 local transposes): checks the CUDA transpose / twiddle kernels and the batched local FFTs inside the
 six-step flow against the oracle and against the single-plan path.  The multi-rank exchange logic is
 covered on CPU (tests/test_distributed_host_logic.py) and by tools/dist_check.py under torchrun."""
+import os
+
 import numpy as np
 import pytest
 
@@ -84,3 +86,12 @@ def test_peer_exchange_kernel_layout(real, forward):
     for q in range(P):
         want = (g * w)[:, q * cb:(q + 1) * cb].t().contiguous().numpy().ravel()
         assert rel_err(outs[q].cpu().numpy(), want) < (5e-7 if real == "f32" else 4e-15)
+
+
+@pytest.mark.skipif(os.environ.get("FOURIER_B200_TEST_EXPERIMENTAL") != "1",
+                    reason="the grid-limited persistent exchange kernel has not run on a GPU yet; "
+                           "set FOURIER_B200_TEST_EXPERIMENTAL=1")
+def test_peer_exchange_kernel_persistent_variant(monkeypatch):
+    monkeypatch.setenv("FOURIER_B200_EXCHANGE_BLOCKS", "7")      # 7 blocks walk 4 * 2 * 1 = 8+ tiles each
+    test_peer_exchange_kernel_layout("f32", True)
+    test_peer_exchange_kernel_layout("f64", None)

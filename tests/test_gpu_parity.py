@@ -236,6 +236,23 @@ def test_alternative_persistent_kernel_configurations(monkeypatch, real, n, cfg)
         assert rel_err(got[7], O.transform(x[7], int(code))) < TOL[real]
 
 
+@pytest.mark.skipif(os.environ.get("FOURIER_B200_TEST_EXPERIMENTAL") != "1",
+                    reason="variants 5-7 (blocked intermediate, direct loads) are verified by CPU emulation only so "
+                           "far; set FOURIER_B200_TEST_EXPERIMENTAL=1 to run them on the GPU")
+@pytest.mark.parametrize("real,n", [("f32", 1 << 20), ("f64", 1 << 16)])
+@pytest.mark.parametrize("cfg", [5, 6, 7])
+def test_experimental_persistent_kernel_configurations(monkeypatch, real, n, cfg):
+    monkeypatch.setenv("FOURIER_B200_CFG", str(cfg))
+    x = O.fill_input(40, n, NP[real], first_transform=2)
+    alt = create(real, n)
+    monkeypatch.delenv("FOURIER_B200_CFG")
+    ref = create(real, n)
+    for code in (T.Fft, T.Ifft):
+        got = gpu_transform(alt, x, code)
+        assert rel_err(got, gpu_transform(ref, x, code)) < TOL[real]
+        assert rel_err(got[7], O.transform(x[7], int(code))) < TOL[real]
+
+
 def test_error_conventions():
     L = _lib.load()
     assert not L.fourier_create_float(0)          # reference hangs on 0 (autosort/mod.rs:112): refused
