@@ -176,8 +176,9 @@ def run_distributed(args, rank, local_rank, world, barrier):
     x, s = plan.buffers()
     fb.fill_input(x.view(1, blk), first_transform=rank)
     cur, oth = x, s
+    natural = not args.transposed_output
     for _ in range(args.warmup):
-        out = plan.transform(cur, oth)
+        out = plan.transform(cur, oth, natural_order=natural)
         cur, oth = (out, oth if out is cur else cur)
     barrier()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -185,7 +186,7 @@ def run_distributed(args, rank, local_rank, world, barrier):
         barrier()
         start.record()
         for _ in range(args.steps):
-            out = plan.transform(cur, oth)
+            out = plan.transform(cur, oth, natural_order=natural)
             cur, oth = (out, oth if out is cur else cur)
         stop.record()
         barrier()
@@ -195,11 +196,12 @@ def run_distributed(args, rank, local_rank, world, barrier):
     if rank != 0:
         return
     ms_per_step = float(ms.item()) / args.steps
-    wire = plan.wire_bytes_per_exchange(8) * 3
+    n_exchanges = 3 if natural else 2
+    wire = plan.wire_bytes_per_exchange(8) * n_exchanges
     peak, peak_src = measured_peak()
     # per GPU and step, read + write each: 2 FFT batches and 3 exchanges (one sweep each over NVLink peer memory;
     # pack + all_to_all + unpack = 3 sweeps with NCCL)
-    sweeps = 2 + (3 if plan.exchange == "peer" else 9)
+    sweeps = 2 + n_exchanges * (1 if plan.exchange == "peer" else 3)
     local_bytes = blk * 8 * 2 * sweeps
     achieved = local_bytes / (ms_per_step * 1e-3) / 1e9
     print(json.dumps({
@@ -214,6 +216,7 @@ def run_distributed(args, rank, local_rank, world, barrier):
                                    if plan.exchange == "peer" else
                                    f"block-distributed over {world} ranks, 3 NCCL all-to-all transposes, each "
                                    f"pipelined in {plan.chunks} pieces"),
+                   "output": "natural order" if natural else "transposed (Y[k1][k2] = X[k1 + n1*k2], last exchange skipped)",
                    "note": "successive steps transform the previous result (ping-pong buffers)"},
         "nvlink": {"bytes_sent_per_gpu_per_step": wire,
                    "achieved_gbs_per_gpu_per_direction_if_exchanges_were_the_whole_step": wire / (ms_per_step * 1e-3) / 1e9,
@@ -238,6 +241,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--verify", type=int, default=4, help="transforms checked against the oracle")
     ap.add_argument("--log2n", type=int, default=30, help="c5 only: log2 of the distributed transform length")
+    ap.add_argument("--transposed-output", action="store_true",
+                    help="c5 only: leave the result transposed (2 exchanges instead of 3)")
     ap.add_argument("--chunks", type=int, default=0, help="c5 only: row blocks per pipelined exchange (0 = plan default)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="c5 only: exchanges as one kernel over NVLink peer memory, or pack + NCCL all_to_all + unpack")

@@ -335,18 +335,27 @@ class DistributedFft:
             raise ValueError("exchange='peer': transform() needs the plan's own buffers (plan.buffers())")
         return table
 
-    def transform(self, x, scratch, forward=True):
+    def transform(self, x, scratch, forward=True, natural_order=True):
         """x: this rank's N/P samples (its block of the natural order), scratch: same size.  Both are
         clobbered; returns the one holding this rank's block of the result (unscaled in both directions:
-        Transform.Fft / Transform.UnscaledIfft)."""
+        Transform.Fft / Transform.UnscaledIfft).
+
+        natural_order=False skips the third exchange (a third of the NVLink traffic): the result stays
+        transposed, rank r holding rows k1 in [r*N1/P, (r+1)*N1/P) of Y[k1][k2] = X[k1 + N1*k2] -- enough for
+        callers that can consume the spectrum in that order."""
         P, be = self.world, self.backend
         n1, n2 = self.n1, self.n2
         r1, r2 = n1 // P, n2 // P
         if self.exchange == "peer":
             a = self._fft_then_exchange(x, scratch, r1, n2, 0, forward, None)                          # [n2_loc][n1]
             b = self._fft_then_exchange(a, x, r2, n1, n1, forward, (forward, self.rank * r2, self.n))  # [k1_loc][n2]
+            if not natural_order:
+                be.fft_rows(b, n2, forward)
+                return b                                                                               # [k1_loc][k2]
             return self._fft_then_exchange(b, scratch, r1, n2, n2, forward, None)                      # [k2_loc][k1]
         a = self._exchange(x, scratch, r1, n2, then=lambda rows, first: be.fft_rows(rows, n1, forward))   # [n2_loc][k1]
         b = self._exchange(a, x, r2, n1, twiddle=(forward, self.rank * r2, self.n),
                            then=lambda rows, first: be.fft_rows(rows, n2, forward))                       # [k1_loc][k2]
+        if not natural_order:
+            return b
         return self._exchange(b, scratch, r1, n2)                                                         # [k2_loc][k1]

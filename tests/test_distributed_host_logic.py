@@ -23,7 +23,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, n1, n2, forward, q):
+def _worker(rank, world, port, n1, n2, forward, q, natural_order=True):
     sys.path.insert(0, ROOT)
     from fourier_b200.distributed import DistributedFft, NumpyBackend
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -36,9 +36,14 @@ def _worker(rank, world, port, n1, n2, forward, q):
     x = torch.from_numpy(full[rank * blk:(rank + 1) * blk].copy())
     scratch = torch.empty_like(x)
     plan = DistributedFft(n1, n2, rank, world, NumpyBackend())
-    out = plan.transform(x, scratch, forward=forward)
+    out = plan.transform(x, scratch, forward=forward, natural_order=natural_order)
     want = np.fft.fft(full) if forward else np.fft.ifft(full) * n
-    err = np.abs(out.numpy() - want[rank * blk:(rank + 1) * blk]).max() / np.abs(want).max()
+    if natural_order:
+        mine = want[rank * blk:(rank + 1) * blk]
+    else:                                   # transposed result: rows k1 of Y[k1][k2] = X[k1 + n1*k2]
+        r1 = n1 // world
+        mine = want.reshape(n2, n1).T[rank * r1:(rank + 1) * r1].ravel()
+    err = np.abs(out.numpy() - mine).max() / np.abs(want).max()
     q.put((rank, float(err)))
     dist.destroy_process_group()
 
@@ -49,6 +54,21 @@ def test_six_step_exchange_logic(world, n1, n2, forward):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, n1, n2, forward, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    errs = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert len(errs) == world and max(errs.values()) < 1e-12, errs
+
+
+def test_transposed_output_skips_the_last_exchange():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world, n1, n2 = 2, 16, 8
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n1, n2, True, q, False)) for r in range(world)]
     for p in procs:
         p.start()
     errs = dict(q.get(timeout=180) for _ in range(world))
