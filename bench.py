@@ -210,11 +210,12 @@ def run_distributed(args, rank, local_rank, world, barrier):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS["c5"][3], "N": n, "n1": n1, "n2": n2,
-                   "parallelism": (f"block-distributed over {world} ranks, 3 exchanges, each ONE transposing kernel storing "
-                                   "into the peers' buffers over NVLink (CUDA IPC) + a stream-ordered barrier; the "
-                                   f"exchange of a row block overlaps the FFTs of the next ({plan.chunks} blocks)"
+                   "parallelism": (f"block-distributed over {world} ranks, {n_exchanges} exchanges, each ONE transposing kernel storing "
+                                   "into the peers' buffers over NVLink (CUDA IPC) + a stream-ordered barrier"
+                                   + (f"; the exchange of a row block overlaps the FFTs of the next ({plan.chunks} blocks)"
+                                      if plan.chunks > 1 else "")
                                    if plan.exchange == "peer" else
-                                   f"block-distributed over {world} ranks, 3 NCCL all-to-all transposes, each "
+                                   f"block-distributed over {world} ranks, {n_exchanges} NCCL all-to-all transposes, each "
                                    f"pipelined in {plan.chunks} pieces"),
                    "output": "natural order" if natural else "transposed (Y[k1][k2] = X[k1 + n1*k2], last exchange skipped)",
                    "note": "successive steps transform the previous result (ping-pong buffers)"},
