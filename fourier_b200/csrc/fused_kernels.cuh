@@ -168,7 +168,9 @@ template <typename T> struct FusedArgs {
 //           A[k1][n2].  A pass-1 tile then writes 256-byte runs (a warp's store = 4 consecutive k1 x 8 columns)
 //           instead of four 64-byte row pieces -- half the LSU wavefronts -- and a pass-2 tile (8 rows k1) is
 //           still one contiguous bulk copy; its threads pick their samples with the block-fast mapping
-//           (tilefft.cuh), under which a warp needs only 8 different stage twiddles (broadcast loads).
+//           (tilefft.cuh), under which a warp needs only 8 different stage twiddles (broadcast loads).  The base
+//           table of the factored inter-pass twiddle is [tile][p][col] in this mode (its [col][p] load is an
+//           8-way bank conflict, once per tile).
 //           Verified by CPU emulation (tools/emulate.cu); NOT yet run or measured on the GPU.
 // DIRECT_:  1 = no shared-memory staging at all: the consumers load their samples from global memory straight into
 //           registers (pass 1: the input, which the producer lane has prefetched into L2 one tile period ahead with
@@ -340,7 +342,7 @@ template <class Cfg, bool FWD> struct FusedMath {
   // pass 1: inter-pass twiddle (factored, tables tb = [base | step]) and store into the ring slot `slot_base`
   static FB_HD void store1(const Tile& f, int t, V* slot_base, int tile, const V* tb) {
     if constexpr (Cfg::BLOCKED)
-      f.template store_factored<N2, 1, 2, N2 * 8>(t, slot_base + (size_t)tile * 64, tb, tb + C * R);
+      f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * 64, tb, tb + C * R);
     else
       f.template store_factored<N2, 1, 2>(t, slot_base + (size_t)tile * C, tb, tb + C * R);   // keep in L2
   }

@@ -239,7 +239,8 @@ struct TileFFT {
   // BLOCK_ROW > 0: the destination is the blocked intermediate [k / 8][tile][k % 8][col] with BLOCK_ROW
   // elements per k-block row (= 64 * tiles per row) and `base` pointing at the tile's block of row 0: the 4
   // consecutive k of a warp and its 8 columns form one 256-byte run.
-  template <long KS, long CS, int HINT, long BLOCK_ROW = 0>
+  // BASE_PCOL: sbase is laid out [p][col] instead of [col][p] (conflict-free for lanes = 8 columns x 4 p).
+  template <long KS, long CS, int HINT, long BLOCK_ROW = 0, bool BASE_PCOL = false>
   FB_HD void store_factored(int t, V* __restrict__ base, const V* sbase, const V* sstep) const {
     const int col = col_of<false>(t), u = u_of<false>(t);
     static_assert(BLOCK_ROW == 0 || (C == 8 && RA % 8 == 0), "blocked intermediate: 8 columns per tile");
@@ -247,7 +248,7 @@ struct TileFFT {
       constexpr int c = decltype(Cc)::value;
       const int p = u + TP * c;
       const long off = BLOCK_ROW ? (long)(p >> 3) * BLOCK_ROW + (p & 7) * 8 + col : (long)col * CS + (long)p * KS;
-      const V wb = sbase[col * RA + p];
+      const V wb = BASE_PCOL ? sbase[p * C + col] : sbase[col * RA + p];
       static_for<0, RB>([&](auto Rr) FB_LAMBDA {
         constexpr int r = decltype(Rr)::value;
         const V w = cmul(wb, sstep[r * C + col]);

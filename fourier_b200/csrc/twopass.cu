@@ -61,6 +61,7 @@ template <typename T> struct FusedOps {
   int ra, rb, tile_c;
   size_t smem_bytes;
   int default_ring, default_lag;
+  bool base_pcol;   // layout of the factored base table this configuration reads (tables.cuh)
   cudaError_t (*prepare)();
   cudaError_t (*launch)(const fused::FusedArgs<T>&, bool fwd, int grid, cudaStream_t);
 };
@@ -96,7 +97,7 @@ template <class Cfg> struct FusedImpl {
   }
   static const FusedOps<T>* ops(int ring, int lag) {
     static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::R, Cfg::R, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
-                                  &prepare, &launch};
+                                  Cfg::BLOCKED, &prepare, &launch};
     return &o;
   }
 };
@@ -172,7 +173,7 @@ cudaError_t Plan<T>::init_twopass() {
       // factored inter-pass twiddles, contiguous per pass-1 tile of `tile_c` columns:
       //   tbase[tile][col][p] = w_N^{n2*p},  tstep[tile][r][col] = w_N^{R*n2*r},  n2 = tile*tile_c + col
       std::vector<cpx<T>> tb, ts;
-      make_factored_twiddles<T>(n_, n2_, f->ra, f->tile_c, tb, ts);
+      make_factored_twiddles<T>(n_, n2_, f->ra, f->tile_c, tb, ts, f->base_pcol);
       FB_CHECK((upload_vec<T, cpx<T>>(tbase_, tb)));
       FB_CHECK((upload_vec<T, cpx<T>>(tstep_, ts)));
       fused_ops_ = f;

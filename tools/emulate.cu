@@ -313,7 +313,7 @@ static int check_fused(const char* name, double tol) {
   }
   auto twa = make_twa<T>(R, R);
   std::vector<V> tbase, tstep;
-  make_factored_twiddles<T>((size_t)N, (size_t)N2, R, C, tbase, tstep);
+  make_factored_twiddles<T>((size_t)N, (size_t)N2, R, C, tbase, tstep, Cfg::BLOCKED);
   int bad = 0;
   for (int fwd = 1; fwd >= 0; --fwd) {
     std::vector<V> x(N), scratch(N), out(N), staging((size_t)C * Cfg::L), tab(2 * (size_t)C * R);
