@@ -105,6 +105,25 @@ def test_no_cpu_fallback_without_a_gpu(libfourier):
     assert not libfourier.fourier_create_double(8)
 
 
+def test_distributed_building_blocks_reject_bad_arguments(libfourier):
+    """Argument validation of the exchange / pack / peer-memory entry points happens before any CUDA call, so it
+    can be checked without a GPU: nonzero return code and a message in fourier_b200_last_error()."""
+    import ctypes
+    L = _lib.load()
+    outs = (ctypes.c_void_p * 2)(None, None)
+    assert L.fourier_b200_exchange_float(None, outs, 2, 0, 8, 8, 16, 16, 0, 0, 0, 0, None) != 0
+    assert "exchange" in _lib.last_error()
+    buf = ctypes.create_string_buffer(64)
+    assert L.fourier_b200_exchange_double(buf, outs, 0, 0, 8, 8, 16, 16, 0, 0, 0, 0, None) != 0      # no ranks
+    assert L.fourier_b200_exchange_double(buf, outs, 2, 2, 8, 8, 16, 16, 0, 0, 0, 0, None) != 0      # rank out of range
+    assert L.fourier_b200_exchange_double(buf, outs, 2, 0, 8, 8, 16, 16, 0, 3, 0, 64, None) != 0     # twiddle mode
+    assert L.fourier_b200_pack_float(buf, buf, 1, 8, 8, 8, 8, 64, 7, 0, 0, 64, None) != 0            # twiddle mode
+    ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+    assert L.fourier_b200_peer_alloc(0, ctypes.byref(ptr), handle) != 0                              # empty buffer
+    assert L.fourier_b200_peer_open(None, ctypes.byref(ptr)) != 0
+    assert L.fourier_b200_peer_close(None) == 0 and L.fourier_b200_peer_free(None) == 0              # no-ops
+
+
 def test_product_never_imports_the_oracle():
     """oracle/ is test infrastructure: nothing under fourier_b200/ may include, import, link or dlopen it
     (comments may mention it)."""
