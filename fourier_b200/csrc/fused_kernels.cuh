@@ -157,43 +157,32 @@ template <typename T> struct FusedArgs {
   long long* trace;           // optional phase timestamps of CTA 0 (debugging / DESIGN.md timeline), else nullptr
 };
 
-// Configuration: N = (R*R)^2, tiles of C FFTs, G consumer groups per CTA.
-// EXB_ > 0: EXB_ separate exchange buffers (group g uses g % EXB_, under a lock when shared); the staging
-//           buffer is released as soon as the samples are in registers.
-// EXB_ = 0: the exchange happens IN PLACE in the group's staging buffer, which is released after the
-//           gather; the refill then overlaps stage B and the stores.  Costs no prefetch distance that
-//           matters (a TMA round trip is shorter than stage B + stores) and frees a third of the shared
-//           memory, i.e. room for one more consumer group.
-// BLOCKED_: the intermediate is stored in 8 x 8 blocks [k1 / 8][n2 / 8][k1 % 8][n2 % 8] instead of row-major
-//           A[k1][n2].  A pass-1 tile then writes 256-byte runs (a warp's store = 4 consecutive k1 x 8 columns)
-//           instead of four 64-byte row pieces -- half the LSU wavefronts -- and a pass-2 tile (8 rows k1) is
-//           still one contiguous bulk copy; its threads pick their samples with the block-fast mapping
-//           (tilefft.cuh), under which a warp needs only 8 different stage twiddles (broadcast loads).  The base
-//           table of the factored inter-pass twiddle is [tile][p][col] in this mode (its [col][p] load is an
-//           8-way bank conflict, once per tile).
-//           Verified by CPU emulation (tools/emulate.cu); NOT yet run or measured on the GPU.
-// DIRECT_:  1 = no shared-memory staging at all: the consumers load their samples from global memory straight into
-//           registers (pass 1: the input, which the producer lane has prefetched into L2 one tile period ahead with
-//           cp.async.bulk.prefetch.tensor; pass 2: the L2-resident blocked intermediate, ld.global.cg).  Saves the
-//           TMA write into shared memory (which stalls the LSU pipe cycle for cycle) and the staging read --
-//           about a third of the LSU wavefronts per tile (profiles/r01_lsu_pipe_analysis.txt) -- and leaves room
-//           for one exchange buffer per group (no lock).  2 = only pass 2 loads directly (its source is always an
-//           L2 hit); pass 1 keeps the TMA staging.  Same verification status as BLOCKED_.
-template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool BLOCKED_ = false, int DIRECT_ = 0>
+// Configuration: N = (R*R)^2, tiles of C = 8 FFTs, G consumer groups per CTA, EXB exchange buffers (group g uses
+// g % EXB, under a lock when shared); the staging buffer is released as soon as the samples are in registers.
+// The intermediate is stored in 8 x 8 blocks [k1 / 8][n2 / 8][k1 % 8][n2 % 8]: a pass-1 tile writes 256-byte runs (a
+// warp's store = 4 consecutive k1 x 8 columns; row-major A[k1][n2] gave four 64-byte pieces and twice the LSU
+// wavefronts: measured +5 % on B200, profiles/r02_persistent_kernel_variants.txt), and a pass-2 tile (8 rows k1) is
+// still one contiguous bulk copy; its threads pick their samples with the block-fast mapping (tilefft.cuh), under
+// which a warp needs only 8 different stage twiddles (broadcast loads).  The base table of the factored inter-pass
+// twiddle is [tile][p][col] (conflict-free for lanes = 8 columns x 4 p).
+// DIRECT_: no shared-memory staging: the consumers load their samples from global memory straight into registers
+//          (pass 1: the input, which the producer lane has prefetched into L2 one tile period ahead with
+//          cp.async.bulk.prefetch.tensor; pass 2: the L2-resident intermediate, ld.global.cg), one exchange buffer
+//          per group and no lock.  Wins for f64 (four 128-thread groups hide the load latency: +4 %), loses for f32
+//          (two 256-thread groups: -12 %), same profile file.
+template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool DIRECT_ = false>
 struct FusedCfg {
   using T = T_;
-  static constexpr bool INPLACE = EXB_ == 0;
-  static constexpr bool BLOCKED = BLOCKED_;
-  static constexpr bool DIRECT_P1 = DIRECT_ == 1, DIRECT_P2 = DIRECT_ != 0;
-  static_assert(DIRECT_ == 0 || (BLOCKED_ && EXB_ != 0), "direct loads: blocked intermediate, separate exchange buffers");
-  static constexpr int R = R_, C = C_, G = G_, EXB = INPLACE ? G_ : EXB_;
+  static constexpr bool DIRECT = DIRECT_;
+  static_assert(!DIRECT_ || EXB_ == G_, "direct loads: one exchange buffer per group");
+  static constexpr int R = R_, C = C_, G = G_, EXB = EXB_;
   static constexpr long L = (long)R * R, N1 = L, N2 = L, N = N1 * N2;
   template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
   using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
-  // pass 2: scatter u-fast (row stride = 1 mod 16 elements) or block-fast (= 2 mod 16 for 8-byte, odd for
-  // 16-byte elements: conflict-free for lanes = 8 positions x 4 FFTs), gather col-fast
-  using Lay2 = ExLayout<R * C + (BLOCKED_ ? (sizeof(T_) == 4 ? 2 : 1) : 1), C, 1>;
-  static_assert(!BLOCKED_ || (C_ == 8 && R_ % 8 == 0), "the blocked intermediate needs 8-column tiles");
+  // pass 2: scatter block-fast (row stride = 2 mod 16 for 8-byte, odd for 16-byte elements: conflict-free for
+  // lanes = 8 positions x 4 FFTs), gather col-fast
+  using Lay2 = ExLayout<R * C + (sizeof(T_) == 4 ? 2 : 1), C, 1>;
+  static_assert(C_ == 8 && R_ % 8 == 0, "the blocked intermediate needs 8-column tiles");
   static constexpr int GT = R * C;                    // threads per group
   static constexpr int CONSUMERS = G * GT;
   static constexpr int AUX = ((G + 1 + 3) / 4) * 128;  // G producer warps + 1 signaller warp, in whole warpgroups
@@ -212,15 +201,12 @@ struct FusedCfg {
   static constexpr int EX_ELEMS = EX1 > EX2 ? EX1 : EX2;
   static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * EX_ELEMS + 127) / 128) * 128;
   static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (R / 2) * R;
-  // per-group buffer: the staged tile, and in the in-place mode also the (slightly larger) exchange
-  static constexpr size_t BUF_BYTES =
-      DIRECT_P1 ? 0 : INPLACE ? (((EX_BYTES > TILE_BYTES ? EX_BYTES : TILE_BYTES) + 1023) / 1024) * 1024 : (size_t)TILE_BYTES;
-  static constexpr int TAB_BUFS = INPLACE ? 1 : 2;   // tile tables: own mbarrier pair (in place) or double buffer
-  // layout: staging[G] | exchange | twa | tile tables [G][TAB_BUFS][base, step] | control
+  static constexpr size_t BUF_BYTES = DIRECT ? 0 : (size_t)TILE_BYTES;   // per-group staging buffer
+  // layout: staging[G] | exchange[EXB] | twa | tile tables [G][2 (double buffer)][base, step] | control
   static constexpr size_t OFF_EX = (size_t)G * BUF_BYTES;
-  static constexpr size_t OFF_TWA = OFF_EX + (INPLACE ? 0 : (size_t)EXB * EX_BYTES);
+  static constexpr size_t OFF_TWA = OFF_EX + (size_t)EXB * EX_BYTES;
   static constexpr size_t OFF_TAB = OFF_TWA + TWA_BYTES;
-  static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * TAB_BUFS * 2 * TAB_BYTES;
+  static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 2 * 2 * TAB_BYTES;
   static constexpr size_t SMEM_BYTES = OFF_CTL + 1024 /* control block: G * sizeof(GroupCtl) + locks */;
   static constexpr int BOX_ROWS = L < 256 ? (int)L : 256;   // TMA box limit: 256 per dimension
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
@@ -231,8 +217,6 @@ constexpr int kStoreRing = 16;
 struct GroupCtl {            // per-group control block in shared memory
   uint64_t full;             // TMA for the group's next tile has landed
   uint64_t empty;            // every thread of the group is done with the staging buffer
-  uint64_t full_tab;         // in-place mode: the tile tables of the group's next pass-1 tile have landed
-  uint64_t empty_tab;        // in-place mode: every thread of the group has issued the stores that use them
   WorkItem desc;             // the tile the staging buffer holds / will hold
   int loaded;                // warps of the group that have pulled their samples out of staging (this tile)
   unsigned stored_warps;     // warps of the group that have issued the stores of the current pass-1 tile
@@ -253,27 +237,24 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   d.slot = wi.b & (a.ring - 1);               // ring is a power of two
   ctl->desc = d;
   if (wi.pass < 0) { mbar_arrive(&ctl->full); return; }
-  // direct loads: nothing to stage, the consumers read global memory themselves; only the tile tables of a
-  // pass-1 tile travel
-  if (Cfg::DIRECT_P1 && wi.pass == 1) {
+  if constexpr (Cfg::DIRECT) {
+    // nothing to stage, the consumers read global memory themselves; only the tile tables of a pass-1 tile travel
+    if (wi.pass == 2) { mbar_arrive(&ctl->full); return; }
     mbar_arrive_expect_tx(&ctl->full, 2 * Cfg::TAB_BYTES);
     bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
     bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
     return;
   }
-  if (Cfg::DIRECT_P2 && wi.pass == 2) { mbar_arrive(&ctl->full); return; }
   // (the group's reads of `dst` are ordered before this refill by the empty-mbarrier wait of the caller)
   if (wi.pass == 1) {
-    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + (Cfg::INPLACE ? 0 : 2 * Cfg::TAB_BYTES));
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + 2 * Cfg::TAB_BYTES);
     constexpr int BOX = Cfg::BOX_ROWS;
     const int x = wi.tile * C * 2;  // in scalars of T
 #pragma unroll
     for (int r0 = 0; r0 < (int)Cfg::L; r0 += BOX)
       tma_load_2d_first(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), &ctl->full);
-    if constexpr (!Cfg::INPLACE) {
-      bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
-      bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
-    }
+    bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
   } else {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES);
     const V* src = a.scratch + (size_t)d.slot * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
@@ -283,15 +264,6 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
       bulk_load((unsigned char*)dst + o, (const unsigned char*)src + o,
                 Cfg::TILE_BYTES - o < PIECE ? Cfg::TILE_BYTES - o : PIECE, &ctl->full);
   }
-}
-
-// In-place mode: the tile tables of a pass-1 tile travel on their own mbarrier (single buffer per group).
-template <class Cfg>
-__device__ __forceinline__ void issue_tables(const WorkItem& wi, const FusedArgs<typename Cfg::T>& a,
-                                             cpx<typename Cfg::T>* tab, GroupCtl* ctl) {
-  mbar_arrive_expect_tx(&ctl->full_tab, 2 * Cfg::TAB_BYTES);
-  bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::C * Cfg::R, Cfg::TAB_BYTES, &ctl->full_tab);
-  bulk_load(tab + Cfg::C * Cfg::R, a.tstep + (size_t)wi.tile * Cfg::C * Cfg::R, Cfg::TAB_BYTES, &ctl->full_tab);
 }
 
 // Address of the counter a work item depends on (nullptr: no dependency) and the value it must reach.
@@ -312,20 +284,19 @@ template <class Cfg, bool FWD> struct FusedMath {
   using Tile = typename Cfg::template Tile<FWD>;
   static constexpr int C = Cfg::C, R = Cfg::R;
   static constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
-  static constexpr int kMap2 = Cfg::BLOCKED ? kMapBF : kMapUF;     // pass-2 mapping up to the exchange
-  static_assert(!Cfg::BLOCKED || Tile::kBlockFastOk, "tile shape does not fit the block-fast mapping");
+  static constexpr int kMap2 = kMapBF;     // pass-2 mapping up to the exchange
+  static_assert(Tile::kBlockFastOk, "tile shape does not fit the block-fast mapping");
 
-  // staging -> registers.  Pass 1: staging = [n1][C] (TMA box); pass 2: C contiguous rows, or 8 x 8 blocks.
+  // staging -> registers.  Pass 1: staging = [n1][C] (TMA box); pass 2: the tile's 8 x 8 blocks.
   // DIRECT: `stage` is the tile's first sample in global memory: C columns of x (row stride N2, read once), or the
   // tile's 8 x 8 blocks of the intermediate (rewritten by other SMs during the kernel: L2 only).
   static FB_HD void load(Tile& f, int pass, int t, const V* stage) {
     if (pass == 1) {
-      if constexpr (Cfg::DIRECT_P1) f.template load<kMapCF, N2, 1, 1>(t, stage);
+      if constexpr (Cfg::DIRECT) f.template load<kMapCF, N2, 1, 1>(t, stage);
       else f.template load<kMapCF, C, 1>(t, stage);
     } else {
-      if constexpr (Cfg::DIRECT_P2) f.template load_blocked<kMapBF, 2>(t, stage);
-      else if constexpr (Cfg::BLOCKED) f.template load_blocked<kMapBF>(t, stage);
-      else f.template load<kMapUF, 1, N2>(t, stage);
+      if constexpr (Cfg::DIRECT) f.template load_blocked<kMapBF, 2>(t, stage);
+      else f.template load_blocked<kMapBF>(t, stage);
     }
   }
   static FB_HD void stage_a(Tile& f, int pass, int t, const TwPair<T>* twa) {
@@ -340,11 +311,9 @@ template <class Cfg, bool FWD> struct FusedMath {
     else f.template gather<kMapCF, typename Cfg::Lay2>(t, exch);
   }
   // pass 1: inter-pass twiddle (factored, tables tb = [base | step]) and store into the ring slot `slot_base`
+  // (blocked layout, kept in L2)
   static FB_HD void store1(const Tile& f, int t, V* slot_base, int tile, const V* tb) {
-    if constexpr (Cfg::BLOCKED)
-      f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * 64, tb, tb + C * R);
-    else
-      f.template store_factored<N2, 1, 2>(t, slot_base + (size_t)tile * C, tb, tb + C * R);   // keep in L2
+    f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * 64, tb, tb + C * R);
   }
   // pass 2: transposed store of the result, X[k1 + N1 * k2], streaming
   static FB_HD void store2(const Tile& f, int t, V* out_b, int tile, bool do_scale, T scale) {
@@ -373,7 +342,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   using T = typename Cfg::T;
   using V = cpx<T>;
   constexpr int G = Cfg::G, GT = Cfg::GT, C = Cfg::C, R = Cfg::R;
-  constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2, L = Cfg::L;
+  constexpr long N = Cfg::N, N2 = Cfg::N2;
   constexpr int T1 = Cfg::T1, T2 = Cfg::T2;
   using Tile = typename Cfg::template Tile<FWD>;
   using Math = FusedMath<Cfg, FWD>;
@@ -385,7 +354,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   unsigned char* staging = base;                                             // [G][BUF_BYTES]
   unsigned char* exch_pool = base + Cfg::OFF_EX;
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
-  V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][TAB_BUFS][2][C*R]
+  V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][2][2][C*R]
   GroupCtl* ctl_all = reinterpret_cast<GroupCtl*>(base + Cfg::OFF_CTL);
   int* locks = reinterpret_cast<int*>(ctl_all + G);   // one per exchange buffer
 
@@ -394,8 +363,6 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     for (int g = 0; g < G; ++g) {
       mbar_init(&ctl_all[g].full, 1);
       mbar_init(&ctl_all[g].empty, GT);
-      mbar_init(&ctl_all[g].full_tab, 1);
-      mbar_init(&ctl_all[g].empty_tab, GT);
       ctl_all[g].loaded = 0;
       ctl_all[g].stored_warps = 0;
       ctl_all[g].stored_seq = 0;
@@ -424,7 +391,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       const int g = pw;
       GroupCtl* ctl = &ctl_all[g];
       V* stage_g = reinterpret_cast<V*>(staging + (size_t)g * Cfg::BUF_BYTES);
-      V* tab_g = tabs + (size_t)g * Cfg::TAB_BUFS * 2 * C * R;
+      V* tab_g = tabs + (size_t)g * 2 * 2 * C * R;
       uint32_t n_p1 = 0;
       unsigned w_next = atomicAdd(queue, 1u);
       for (uint32_t it = 0;; ++it) {
@@ -436,7 +403,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
         if (dep) { spin_until_ge(dep, target); fence_proxy_async(); }
         FB_PTRACE(1);
         if (it > 0) mbar_wait(&ctl->empty, (it - 1) & 1);
-        if constexpr (Cfg::DIRECT_P1) {
+        if constexpr (Cfg::DIRECT) {
           // The group has just started on the previous item, so it will ask for this tile one tile period from now
           // (~5 us): long enough for HBM -> L2, short enough that the prefetched tiles of all groups (148 x G x 64 KB)
           // do not crowd the intermediate out of L2.
@@ -447,17 +414,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
           }
         }
         FB_PTRACE(2);
-        if constexpr (Cfg::INPLACE) {
-          // the buffer was last written by the group's own (generic-proxy) exchange stores
-          fence_proxy_async();
-          issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g, ctl);
-          if (wi.pass == 1) {
-            if (n_p1 > 0) mbar_wait(&ctl->empty_tab, (n_p1 - 1) & 1);   // the previous pass-1 tile has stored
-            issue_tables<Cfg>(wi, a, tab_g, ctl);
-          }
-        } else {
-          issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
-        }
+        issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
         FB_PTRACE(3);
         n_p1 += wi.pass == 1;
         if (wi.pass < 0) break;
@@ -501,10 +458,10 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   const int g = tid / GT;
   const int t = tid - g * GT;
   V* stage_g = reinterpret_cast<V*>(staging + (size_t)g * Cfg::BUF_BYTES);
-  V* tab_g = tabs + (size_t)g * Cfg::TAB_BUFS * 2 * C * R;
+  V* tab_g = tabs + (size_t)g * 2 * 2 * C * R;
   GroupCtl* ctl = &ctl_all[g];
   const int bar_id = 1 + g;
-  V* exch = Cfg::INPLACE ? stage_g : reinterpret_cast<V*>(exch_pool + (size_t)(g % Cfg::EXB) * Cfg::EX_BYTES);
+  V* exch = reinterpret_cast<V*>(exch_pool + (size_t)(g % Cfg::EXB) * Cfg::EX_BYTES);
   int* lock = &locks[g % Cfg::EXB];
   constexpr bool kLocked = Cfg::EXB < G;   // several groups share one exchange buffer
   uint32_t k_p1 = 0;   // pass-1 tiles consumed so far by this group: selects the tile-table buffer
@@ -517,70 +474,67 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     FB_TRACE(1);
     if (a.trace && blockIdx.x == 0 && t == 0 && k < kTraceTiles) a.trace[((long)g * (GT / 32) * kTraceTiles + k) * kTracePhases + 7] = wi.pass;
 
-    // ---- staging -> registers; the staging buffer is free again as soon as every thread has its samples ----
+    // ---- staging (or global memory) -> registers; the staging buffer is free again as soon as every thread has
+    // its samples ----
+    const V* ring_rows = a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2;   // pass 2: the tile's rows
     Tile f;
-    if (Cfg::DIRECT_P1 && wi.pass == 1) Math::load(f, 1, t, a.in + (size_t)wi.b * N + (size_t)wi.tile * C);
-    else if (Cfg::DIRECT_P2 && wi.pass == 2) Math::load(f, 2, t, a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);
+    if constexpr (Cfg::DIRECT) Math::load(f, wi.pass, t, wi.pass == 1 ? a.in + (size_t)wi.b * N + (size_t)wi.tile * C : ring_rows);
     else Math::load(f, wi.pass, t, stage_g);
-    if constexpr (!Cfg::INPLACE) mbar_arrive(&ctl->empty);
-    if (!Cfg::DIRECT_P2 && wi.pass == 2) {
-      // The intermediate rows this tile just consumed are dead: drop them from L2 instead of letting the
-      // cache write them back to HBM later (measured: without this ~80% of the intermediate is written
-      // back at RING = 8; the slot is completely rewritten before it is read again).
-      const unsigned char* rows = reinterpret_cast<const unsigned char*>(
-          a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);
-      for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
-    }
-    if (!Cfg::DIRECT_P2 && wi.pass == 2 && (t & 31) == 0) {
-      // the last warp of the group to have pulled its samples reports the ring slot as consumed by this
-      // tile -- promptly and from the consumer side (a lazy report by the producer could deadlock it
-      // against its own dependency wait)
-      if (atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
+    mbar_arrive(&ctl->empty);
+    if constexpr (!Cfg::DIRECT) {
+      if (wi.pass == 2) {
+        // The intermediate rows this tile just consumed are dead: drop them from L2 instead of letting the
+        // cache write them back to HBM later (measured: without this ~80% of the intermediate is written
+        // back at RING = 8; the slot is completely rewritten before it is read again).
+        const unsigned char* rows = reinterpret_cast<const unsigned char*>(ring_rows);
+        for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
+        // the last warp of the group to have pulled its samples reports the ring slot as consumed by this
+        // tile -- promptly and from the consumer side (a lazy report by the producer could deadlock it
+        // against its own dependency wait)
+        if ((t & 31) == 0 && atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
+      }
     }
     FB_TRACE(2);
 
     Math::stage_a(f, wi.pass, t, twa);
-    if (Cfg::DIRECT_P2 && wi.pass == 2 && (t & 31) == 0) {
+    if constexpr (Cfg::DIRECT) {
       // same report with direct loads: stage A has consumed every register the warp loaded, so its global loads
       // have completed
-      if (atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
+      if (wi.pass == 2 && (t & 31) == 0 && atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
     }
 
-    // ---- exchange through the shared buffer, under the CTA-wide lock -----------------------------------------
+    // ---- exchange through the shared buffer (under the CTA-wide lock when the groups share one) ----------------
     if (kLocked && t == 0) {
       unsigned spins = 0;
       while (atomicCAS(lock, 0, 1) != 0) if (++spins > (1u << 26)) __trap();
     }
     FB_TRACE(3);
     group_sync(bar_id, GT);
-    if (Cfg::DIRECT_P2 && wi.pass == 2) {
-      // every warp of the group is past stage A, i.e. all loads of the tile have completed: drop its rows from L2
-      const unsigned char* rows = reinterpret_cast<const unsigned char*>(
-          a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2);
-      for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
-        asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
+    if constexpr (Cfg::DIRECT) {
+      if (wi.pass == 2) {
+        // every warp of the group is past stage A, i.e. all loads of the tile have completed: drop its rows from L2
+        const unsigned char* rows = reinterpret_cast<const unsigned char*>(ring_rows);
+        for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
+          asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
+      }
     }
     Math::scatter(f, wi.pass, t, exch);
     FB_TRACE(4);
     group_sync(bar_id, GT);
     Math::gather(f, wi.pass, t, exch);
-    if constexpr (Cfg::INPLACE) {
-      mbar_arrive(&ctl->empty);   // the buffer may be refilled once every thread has gathered
-    } else {
+    if constexpr (kLocked) {
       group_sync(bar_id, GT);
-      if (kLocked && t == 0) { __threadfence_block(); atomicExch(lock, 0); }
+      if (t == 0) { __threadfence_block(); atomicExch(lock, 0); }
     }
     FB_TRACE(5);
 
     // ---- stage B and the stores ---------------------------------------------------------------------------------
     f.stage_b();
     if (wi.pass == 1) {
-      const V* tb = tab_g + (Cfg::INPLACE ? 0 : (size_t)(k_p1 & 1) * 2 * C * R);
-      if constexpr (Cfg::INPLACE) mbar_wait(&ctl->full_tab, k_p1 & 1);
+      const V* tb = tab_g + (size_t)(k_p1 & 1) * 2 * C * R;
       ++k_p1;
       Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb);
-      if constexpr (Cfg::INPLACE) mbar_arrive(&ctl->empty_tab);
       // report "stores issued"; the last warp of the group hands the tile to the signaller warp
       __syncwarp();
       if ((t & 31) == 0 && atom_add_acq_rel_cta_shared(&ctl->stored_warps, 1u) == GT / 32 - 1) {

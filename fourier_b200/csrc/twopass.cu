@@ -97,45 +97,26 @@ template <class Cfg> struct FusedImpl {
   }
   static const FusedOps<T>* ops(int ring, int lag) {
     static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::R, Cfg::R, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
-                                  Cfg::BLOCKED, &prepare, &launch};
+                                  true, &prepare, &launch};
     return &o;
   }
 };
 
 template <typename T> const FusedOps<T>* fused_lookup(size_t n);
-// FOURIER_B200_CFG selects an alternative configuration of the persistent kernel (experiments; 0 = default).
+// FOURIER_B200_CFG=1 selects the other load strategy (experiments; profiles/r02_persistent_kernel_variants.txt).
 template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
   if (n == ((size_t)1 << 20)) {
-    switch (env_int("FOURIER_B200_CFG", 0)) {
-      // two 256-thread groups on 8-column tiles, one shared exchange buffer taken under a lock
-      case 1: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
-      // four 128-thread groups on 4-column tiles, two exchange buffers
-      case 2: return FusedImpl<fused::FusedCfg<float, 32, 4, 4, 4, 2>>::ops(8, 4);
-      // exchange in place in the staging buffer: two groups / three groups
-      case 3: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 0>>::ops(8, 4);
-      case 4: return FusedImpl<fused::FusedCfg<float, 32, 8, 3, 8, 0>>::ops(16, 6);
-      // default shape with the intermediate in 8 x 8 blocks (CPU-emulated only so far, see FusedCfg)
-      case 5: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1, true>>::ops(8, 4);
-      // blocked intermediate + direct global->register loads (no staging), one exchange buffer per group
-      case 6: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 2, true, 1>>::ops(8, 4);
-      // blocked intermediate + direct loads in pass 2 only (pass 1 keeps the TMA staging, shared exchange buffer)
-      case 7: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1, true, 2>>::ops(8, 4);
-      default: return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
-    }
+    // default: two 256-thread groups, TMA staging, one shared exchange buffer taken under a lock
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 2, true>>::ops(8, 4);
+    return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
   }
   return nullptr;
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
   if (n == ((size_t)1 << 16)) {
-    switch (env_int("FOURIER_B200_CFG", 0)) {
-      case 1: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
-      case 3: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 0>>::ops(64, 32);
-      case 4: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 0>>::ops(128, 48);
-      case 5: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3, true>>::ops(64, 32);
-      case 6: return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true, 1>>::ops(64, 32);
-      case 7: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3, true, 2>>::ops(64, 32);
-      default: return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
-    }
+    // default: four 128-thread groups loading directly from global memory, one exchange buffer each
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
+    return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>::ops(64, 32);
   }
   return nullptr;
 }

@@ -88,9 +88,6 @@ def test_peer_exchange_kernel_layout(real, forward):
         assert rel_err(outs[q].cpu().numpy(), want) < (5e-7 if real == "f32" else 4e-15)
 
 
-@pytest.mark.skipif(os.environ.get("FOURIER_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="the grid-limited persistent exchange kernel has not run on a GPU yet; "
-                           "set FOURIER_B200_TEST_EXPERIMENTAL=1")
 def test_peer_exchange_kernel_persistent_variant(monkeypatch):
     monkeypatch.setenv("FOURIER_B200_EXCHANGE_BLOCKS", "7")      # 7 blocks walk 4 * 2 * 1 = 8+ tiles each
     test_peer_exchange_kernel_layout("f32", True)

@@ -221,28 +221,10 @@ def test_fused_paths_agree_with_general_path(real, n):
 
 
 @pytest.mark.parametrize("real,n", [("f32", 1 << 20), ("f64", 1 << 16)])
-@pytest.mark.parametrize("cfg", [1, 2, 3, 4])
-def test_alternative_persistent_kernel_configurations(monkeypatch, real, n, cfg):
-    # FOURIER_B200_CFG (read when the plan is created) selects the experimental variants of the persistent
-    # two-pass kernel: shared/own exchange buffers, exchange in place, 2..4 consumer groups
-    monkeypatch.setenv("FOURIER_B200_CFG", str(cfg))
-    x = O.fill_input(40, n, NP[real], first_transform=2)
-    alt = create(real, n)
-    monkeypatch.delenv("FOURIER_B200_CFG")
-    ref = create(real, n)
-    for code in (T.Fft, T.Ifft):
-        got = gpu_transform(alt, x, code)
-        assert rel_err(got, gpu_transform(ref, x, code)) < TOL[real]
-        assert rel_err(got[7], O.transform(x[7], int(code))) < TOL[real]
-
-
-@pytest.mark.skipif(os.environ.get("FOURIER_B200_TEST_EXPERIMENTAL") != "1",
-                    reason="variants 5-7 (blocked intermediate, direct loads) are verified by CPU emulation only so "
-                           "far; set FOURIER_B200_TEST_EXPERIMENTAL=1 to run them on the GPU")
-@pytest.mark.parametrize("real,n", [("f32", 1 << 20), ("f64", 1 << 16)])
-@pytest.mark.parametrize("cfg", [5, 6, 7])
-def test_experimental_persistent_kernel_configurations(monkeypatch, real, n, cfg):
-    monkeypatch.setenv("FOURIER_B200_CFG", str(cfg))
+def test_alternative_persistent_kernel_configuration(monkeypatch, real, n):
+    # FOURIER_B200_CFG=1 (read when the plan is created) selects the other load strategy of the persistent two-pass
+    # kernel: direct global loads for f32 (default: TMA staging), TMA staging for f64 (default: direct loads)
+    monkeypatch.setenv("FOURIER_B200_CFG", "1")
     x = O.fill_input(40, n, NP[real], first_transform=2)
     alt = create(real, n)
     monkeypatch.delenv("FOURIER_B200_CFG")

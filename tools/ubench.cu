@@ -85,7 +85,8 @@ template <typename F> float time_ms(F f, int reps = 5) {
   return best;
 }
 
-int main() {
+int main(int argc, char** argv) {
+  const bool bw_only = argc > 1 && argv[1][0] == 'b';
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
   int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   printf("device %s SMs %d clock %d kHz L2 %d MB\n", p.name, p.multiProcessorCount, clk, p.l2CacheSize >> 20);
@@ -94,7 +95,7 @@ int main() {
   const int iters = 20000;
   const int blocks = sms * 8;
   const char* names[] = {"FFMA x2 scalar", "FADD x2 scalar", "FFMA2 packed", "FADD2 packed", "FMUL x2 scalar"};
-  for (int mode = 0; mode < 5; ++mode) {
+  for (int mode = 0; mode < (bw_only ? 0 : 5); ++mode) {
     float ms = 0;
     if (mode == 0) ms = time_ms([&] { fp_kernel<0><<<blocks, 256>>>(dout, iters, 1.0001f, 0.5f); });
     if (mode == 1) ms = time_ms([&] { fp_kernel<1><<<blocks, 256>>>(dout, iters, 1.0001f, 0.5f); });
@@ -105,7 +106,7 @@ int main() {
     printf("%-16s %8.3f ms  %7.2f Tlane-op/s  (%.1f f32 lane-ops/clk/SM @1.965GHz)\n", names[mode], ms,
            lane_ops / ms * 1e-9, lane_ops / (ms * 1e-3) / sms / 1.965e9);
   }
-  for (int mode = 0; mode < 2; ++mode) {
+  for (int mode = 0; mode < (bw_only ? 0 : 2); ++mode) {
     float ms = mode == 0 ? time_ms([&] { fp64_kernel<0><<<blocks, 256>>>((double*)dout, iters / 4, 1.0001, 0.5); })
                          : time_ms([&] { fp64_kernel<1><<<blocks, 256>>>((double*)dout, iters / 4, 1.0001, 0.5); });
     double lane_ops = (double)blocks * 256 * (iters / 4) * 8;
