@@ -63,6 +63,7 @@ class Fft:
         if not self._plan:
             raise RuntimeError(f"fourier_create_{self._t}({size}) returned NULL: {_lib.last_error()}")
         self._size = int(size)
+        self._device = self.info()["device"]
 
     # -- lifetime -------------------------------------------------------------------------------
     def close(self):
@@ -88,6 +89,10 @@ class Fft:
         d["inner_path_name"] = _lib.load().fourier_b200_path_name(i.inner_path).decode()
         return d
 
+    def kernel_name(self):
+        """The kernel that moves (nearly) all of this plan's bytes, as a profiler lists it."""
+        return getattr(_lib.load(), f"fourier_b200_plan_kernel_{self._t}")(self._plan).decode()
+
     def _describe(self, x):
         """-> (pointer, batch, is_device, stream)"""
         if _is_torch(x):
@@ -101,6 +106,8 @@ class Fft:
                 raise ValueError(f"last dimension must be {self._size}")  # assert_eq!, fft.rs:57-58
             batch = x.numel() // self._size
             if x.is_cuda:
+                if x.device.index != self._device:
+                    raise ValueError(f"plan lives on cuda:{self._device}, buffer on {x.device}")
                 return x.data_ptr(), batch, True, torch.cuda.current_stream(x.device).cuda_stream
             return x.data_ptr(), batch, False, None
         if not isinstance(x, np.ndarray):

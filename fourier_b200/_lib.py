@@ -27,7 +27,7 @@ EXTENSION_SYMBOLS = (
      "fourier_b200_path_name", "fourier_b200_last_error", "fourier_b200_version"]
     + [f"fourier_b200_{op}_{t}" for t in ("float", "double")
        for op in ("transform_batch", "transform_batch_async", "plan_info", "create_general", "fill_input",
-                  "transpose", "pack", "exchange", "swap_leading", "twiddle_rows")])
+                  "transpose", "pack", "exchange", "swap_leading", "twiddle_rows", "plan_kernel")])
 
 
 def load():
@@ -52,6 +52,8 @@ def load():
         getattr(L, f"fourier_b200_transform_batch_{t}").argtypes = [vp, vp, vp, sz, ci]
         getattr(L, f"fourier_b200_transform_batch_async_{t}").argtypes = [vp, vp, vp, sz, ci, vp]
         getattr(L, f"fourier_b200_plan_info_{t}").argtypes = [vp, ctypes.POINTER(PlanInfo)]
+        getattr(L, f"fourier_b200_plan_kernel_{t}").restype = ctypes.c_char_p
+        getattr(L, f"fourier_b200_plan_kernel_{t}").argtypes = [vp]
         getattr(L, f"fourier_b200_create_general_{t}").restype = vp
         getattr(L, f"fourier_b200_create_general_{t}").argtypes = [sz]
         getattr(L, f"fourier_b200_fill_input_{t}").argtypes = [vp, ctypes.c_ulonglong, sz, ctypes.c_ulonglong, vp]

@@ -9,6 +9,7 @@
 #include "../../include/fourier_b200.h"
 #pragma GCC visibility pop
 
+#include <cstdint>
 #include <new>
 
 #include "plan.h"
@@ -34,6 +35,18 @@ bool is_device_pointer(const void* p) {
     return false;
   }
   return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// The kernels read and write device buffers with 16-byte vector accesses (cpx<double> as double2, f32 pairs as
+// float4, TMA tensor maps on the input): a misaligned device pointer would fault and poison the CUDA context, so it
+// is refused up front.  (cudaMalloc and torch allocations are 256/512-byte aligned; a slice starting at an odd f32
+// sample is not.)  Host pointers are staged through the library's own buffers and may have any alignment.
+bool device_pointers_aligned(const void* in, const void* out) {
+  if ((((uintptr_t)in) | ((uintptr_t)out)) & 15) {
+    fb200::set_last_error("device buffers must be 16-byte aligned");
+    return false;
+  }
+  return true;
 }
 
 template <typename T>
@@ -63,6 +76,7 @@ int transform_batch(const void* plan, const void* in, void* out, size_t batch, i
       return (int)cudaErrorInvalidValue;
     }
     if (!din) return (int)p->exec_host((const C*)in, (C*)out, batch, code);
+    if (!device_pointers_aligned(in, out)) return (int)cudaErrorMisalignedAddress;
     cudaError_t e = p->exec_device((const C*)in, (C*)out, batch, code, cudaStreamPerThread);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaStreamSynchronize(cudaStreamPerThread);
@@ -78,6 +92,7 @@ int transform_async(const void* plan, const void* in, void* out, size_t batch, i
   auto* p = const_cast<Plan<T>*>(static_cast<const Plan<T>*>(plan));
   using C = typename Plan<T>::C;
   try {
+    if (!device_pointers_aligned(in, out)) return (int)cudaErrorMisalignedAddress;
     return (int)p->exec_device((const C*)in, (C*)out, batch, code, (cudaStream_t)stream);
   } catch (...) {
     fb200::set_last_error("transform threw");
@@ -180,6 +195,12 @@ int fourier_b200_plan_info_double(const fourier_fft_double* plan, fourier_b200_p
   return plan_info<double>(plan, out);
 }
 const char* fourier_b200_path_name(int path) { return fb200::path_name((fb200::Path)path); }
+const char* fourier_b200_plan_kernel_float(const fourier_fft_float* plan) {
+  return plan ? reinterpret_cast<const Plan<float>*>(plan)->kernel_name() : "";
+}
+const char* fourier_b200_plan_kernel_double(const fourier_fft_double* plan) {
+  return plan ? reinterpret_cast<const Plan<double>*>(plan)->kernel_name() : "";
+}
 
 fourier_fft_float* fourier_b200_create_general_float(size_t size) {
   return static_cast<fourier_fft_float*>(create_plan<float>(size, false));

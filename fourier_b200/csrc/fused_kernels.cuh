@@ -299,8 +299,13 @@ template <class Cfg, bool FWD> struct FusedMath {
       else f.template load_blocked<kMapBF>(t, stage);
     }
   }
+  // `twa`: the stage twiddles in the 8-byte-plane layout (TwPlanes): in both mappings 4 or 8 lanes share a pair
   static FB_HD void stage_a(Tile& f, int pass, int t, const TwPair<T>* twa) {
-    if (pass == 1) f.template stage_a<kMapCF>(t, twa); else f.template stage_a<kMap2>(t, twa);
+    if (pass == 1) f.template stage_a<kMapCF, true>(t, twa); else f.template stage_a<kMap2, true>(t, twa);
+  }
+  // plane layout of the pair table `src` ((R / 2) * R pairs), entry i
+  static FB_HD void relayout_twa(void* planes, const TwPair<T>* src, int i) {
+    TwPlanes<T>::put(planes, (R / 2) * R, i, src[i]);
   }
   static FB_HD void scatter(const Tile& f, int pass, int t, V* exch) {
     if (pass == 1) f.template scatter<kMapCF, typename Cfg::Lay1>(t, exch);
@@ -372,7 +377,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     for (int i = 0; i < Cfg::EXB; ++i) locks[i] = 0;
     fence_barrier_init();
   }
-  for (int i = tid; i < (R / 2) * R; i += Cfg::THREADS) twa[i] = a.twa[i];   // stage-A twiddles live in smem
+  for (int i = tid; i < (R / 2) * R; i += Cfg::THREADS) Math::relayout_twa(twa, a.twa, i);   // stage-A twiddles live in smem
   __syncthreads();
 
   unsigned* queue = a.counters;
@@ -468,7 +473,10 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
 
   for (uint32_t k = 0;; ++k) {
     FB_TRACE(0);
-    mbar_wait(&ctl->full, k & 1);
+    // one lane per warp polls (every poll is a shared-memory transaction on the LSU pipe the kernel is bound by);
+    // __syncwarp orders the other lanes' reads of the staged data after its acquire
+    if ((t & 31) == 0) mbar_wait(&ctl->full, k & 1);
+    __syncwarp();
     const WorkItem wi = ctl->desc;
     if (wi.pass < 0) break;
     FB_TRACE(1);

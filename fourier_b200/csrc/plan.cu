@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 
 namespace fb200 {
 
@@ -108,6 +109,7 @@ struct DeviceGuard {
 
 constexpr size_t kScratchTargetBytes = (size_t)512 << 20;  // per scratch buffer on the general path
 constexpr size_t kHostChunkBytes = (size_t)64 << 20;       // host-pointer pipeline granule
+constexpr size_t kHostSmallBytes = (size_t)1 << 20;        // below this a host call takes the single-stream latency path
 
 }  // namespace
 
@@ -122,11 +124,30 @@ Plan<T>* Plan<T>::create(size_t n, int device, bool allow_fast_paths) {
   }
   Plan<T>* p = new (std::nothrow) Plan<T>();
   if (!p) return nullptr;
-  if (p->init(n, device, allow_fast_paths) != cudaSuccess) {
+  cudaError_t e = cudaErrorUnknown;
+  try {
+    e = p->init(n, device, allow_fast_paths);
+  } catch (const std::exception& ex) {   // e.g. bad_alloc while building an N-entry host table
+    set_last_error(std::string("plan construction threw: ") + ex.what());
+  }
+  if (e != cudaSuccess) {
     delete p;
     return nullptr;
   }
   return p;
+}
+
+template <typename T>
+const char* Plan<T>::kernel_name() const {
+  switch (path_) {
+    case Path::kTrivial: return "scale_copy_kernel";
+    case Path::kOnChip: return "onchip::onchip_fft_kernel";
+    case Path::kTwoPass: return fused_ops_ ? "fused::fused_twopass_kernel" : "twopass::tile_kernel (pass 1 + pass 2)";
+    case Path::kGlobalStages: return "stockham_stage_kernel (one launch per radix stage)";
+    case Path::kBluestein: return "chirp / pointwise kernels around the inner plan's kernels";
+    case Path::kBluesteinFused: return "onchip::bluestein_fused_kernel";
+  }
+  return "?";
 }
 
 template <typename T>
@@ -318,21 +339,39 @@ cudaError_t Plan<T>::exec_bluestein(const C* in, C* out, size_t batch, int code,
 // execution on host pointers: H2D -> transform in place -> D2H, three slots in flight
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
+cudaError_t Plan<T>::host_resources() {
+  for (int i = 0; i < 3; ++i)
+    if (!streams_[i]) FB_CHECK(cudaStreamCreateWithFlags(&streams_[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 9; ++i)
+    if (!events_[i]) FB_CHECK(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
+  return cudaSuccess;
+}
+
+template <typename T>
 cudaError_t Plan<T>::exec_host(const C* in, C* out, size_t batch, int code) {
   if (code < 0 || code > 4) { set_last_error("unknown transform code"); return cudaErrorInvalidValue; }
   if (batch == 0) return cudaSuccess;
   DeviceGuard g(device_);
   constexpr int kSlots = 3;
-  for (int i = 0; i < 3; ++i)
-    if (!streams_[i]) FB_CHECK(cudaStreamCreateWithFlags(&streams_[i], cudaStreamNonBlocking));
-  for (int i = 0; i < 9; ++i)
-    if (!events_[i]) FB_CHECK(cudaEventCreateWithFlags(&events_[i], cudaEventDisableTiming));
+  FB_CHECK(host_resources());
+  const size_t bytes_per = n_ * sizeof(C);
+  if (batch * bytes_per <= kHostSmallBytes) {
+    // Latency path (the reference ABI's single small transform, fourier-ffi/src/lib.rs:46-59): nothing to
+    // pipeline, so one stream, no events, one synchronisation: H2D, kernel(s), D2H back to back.
+    cudaStream_t s = streams_[1];
+    FB_CHECK(stage_[0].reserve(std::max(batch * bytes_per, kHostSmallBytes)));
+    C* dev = (C*)stage_[0].data();
+    FB_CHECK(cudaMemcpyAsync(dev, in, batch * bytes_per, cudaMemcpyHostToDevice, s));
+    FB_CHECK(exec_device(dev, dev, batch, code, s));
+    FB_CHECK(cudaMemcpyAsync(out, dev, batch * bytes_per, cudaMemcpyDeviceToHost, s));
+    FB_CHECK(cudaStreamSynchronize(s));
+    return cudaSuccess;
+  }
   cudaStream_t s_in = streams_[0], s_ex = streams_[1], s_out = streams_[2];
   cudaEvent_t* ev_in = &events_[0];    // [slot] H2D finished
   cudaEvent_t* ev_ex = &events_[3];    // [slot] transform finished
   cudaEvent_t* ev_free = &events_[6];  // [slot] D2H finished, slot reusable
 
-  const size_t bytes_per = n_ * sizeof(C);
   size_t chunk = std::max<size_t>(1, kHostChunkBytes / bytes_per);
   chunk = std::min(chunk, batch);
   const size_t nchunks = (batch + chunk - 1) / chunk;

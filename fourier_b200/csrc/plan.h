@@ -89,6 +89,9 @@ class Plan {
   // Number of kernel launches the last exec_* call issued (bench.py reports it).
   unsigned long long launches() const { return launches_; }
 
+  // Name of the kernel that moves (nearly) all of this plan's bytes -- what a profiler will list first.
+  const char* kernel_name() const;
+
  private:
   Plan() = default;
   cudaError_t init(size_t n, int device, bool allow_fast_paths);
@@ -135,6 +138,7 @@ class Plan {
   DeviceBuffer stage_[3];
   cudaStream_t streams_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t events_[9] = {};
+  cudaError_t host_resources();   // streams and events of the host-pointer path, created once
 };
 
 // thread-local error text for the C ABI

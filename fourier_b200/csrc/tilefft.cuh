@@ -73,6 +73,36 @@ template <int HINT, typename V> FB_HD V ld_hint(const V* p) {
 // Two consecutive twiddles, loaded with one 128-bit (f32) / two 128-bit (f64) instructions.
 template <typename T> struct alignas(2 * sizeof(cpx<T>)) TwPair { cpx<T> a, b; };
 
+// The same table in 8-byte planes, for mappings in which many lanes of a warp read the SAME pair (col fast, block
+// fast): a 16-byte shared-memory load costs a wavefront per quarter-warp even when its lanes hit one address
+// (measured, profiles/r02_lsu_budget.txt: 4 per LDS.128 in pass 1, f64 pairs 8), an 8-byte load of <= 16 distinct
+// words costs one in total.  f32: [a (count cpx)][b (count cpx)];  f64: [a.x][a.y][b.x][b.y] (count doubles each).
+template <typename T> struct TwPlanes;
+template <> struct TwPlanes<float> {
+  static FB_HD void put(void* planes, int count, int idx, const TwPair<float>& w) {
+    cpx<float>* p = static_cast<cpx<float>*>(planes);
+    p[idx] = w.a; p[count + idx] = w.b;
+  }
+  static FB_HD TwPair<float> get(const void* planes, int count, int idx) {
+    const cpx<float>* p = static_cast<const cpx<float>*>(planes);
+    TwPair<float> w; w.a = p[idx]; w.b = p[count + idx];
+    return w;
+  }
+};
+template <> struct TwPlanes<double> {
+  static FB_HD void put(void* planes, int count, int idx, const TwPair<double>& w) {
+    double* p = static_cast<double*>(planes);
+    p[idx] = w.a.x; p[count + idx] = w.a.y; p[2 * count + idx] = w.b.x; p[3 * count + idx] = w.b.y;
+  }
+  static FB_HD TwPair<double> get(const void* planes, int count, int idx) {
+    const double* p = static_cast<const double*>(planes);
+    TwPair<double> w;
+    w.a = mk<double>(p[idx], p[count + idx]);
+    w.b = mk<double>(p[2 * count + idx], p[3 * count + idx]);
+    return w;
+  }
+};
+
 // Table layout for the stage-A twiddles w_L^{j*p}: pair index (p/2)*RB + j holds p even / p odd.
 // Lanes that differ in j read consecutive pairs (UF); lanes that share j broadcast (CF).
 template <int RA, int RB> FB_HD int twa_index(int j, int p_half) { return p_half * RB + j; }
@@ -139,7 +169,8 @@ struct TileFFT {
   }
 
   // DFT_RA over i for each owned j, then the stage twiddle w_L^{j*p} (skipped for p == 0).
-  template <int UF> FB_HD void stage_a(int t, const TwPair<T>* __restrict__ twa) {
+  // PLANES: `twa` is the table in the 8-byte-plane layout (TwPlanes) instead of an array of pairs.
+  template <int UF, bool PLANES = false> FB_HD void stage_a(int t, const TwPair<T>* __restrict__ twa) {
     const int u = u_of<UF>(t);
     static_for<0, NA>([&](auto A) FB_LAMBDA {
       constexpr int a = decltype(A)::value;
@@ -147,7 +178,8 @@ struct TileFFT {
       const int j = u + TP * a;
       static_for<0, RA / 2>([&](auto H) FB_LAMBDA {
         constexpr int h = decltype(H)::value;
-        const TwPair<T> w = twa[twa_index<RA, RB>(j, h)];
+        const TwPair<T> w = PLANES ? TwPlanes<T>::get(twa, (RA / 2) * RB, twa_index<RA, RB>(j, h))
+                                   : twa[twa_index<RA, RB>(j, h)];
         if constexpr (h != 0) v[a * RA + bitrev(2 * h, ilog2(RA))] = ctw<FWD>(v[a * RA + bitrev(2 * h, ilog2(RA))], w.a);
         v[a * RA + bitrev(2 * h + 1, ilog2(RA))] = ctw<FWD>(v[a * RA + bitrev(2 * h + 1, ilog2(RA))], w.b);
       });

@@ -69,9 +69,10 @@ class CudaBackend:
     def fft_rows(self, x, n, forward):
         """In-place batched FFT over rows of length n (unscaled in both directions)."""
         from . import Fft, Transform
-        plan = self._plans.get(n)
+        key = (x.device.index, n)
+        plan = self._plans.get(key)
         if plan is None:
-            plan = self._plans[n] = Fft(n, self.real)
+            plan = self._plans[key] = Fft(n, self.real)
         plan.transform_in_place(x.view(-1, n), Transform.Fft if forward else Transform.UnscaledIfft)
 
     def transpose(self, src, dst, rows, cols):
@@ -347,6 +348,10 @@ class DistributedFft:
         n1, n2 = self.n1, self.n2
         r1, r2 = n1 // P, n2 // P
         if self.exchange == "peer":
+            # Entry barrier: step 1 stores straight into every peer's `scratch`, which may hold the peer's previous
+            # result (natural order) that its stream is still reading: no rank may start storing before every rank's
+            # stream has reached this call.  Stream-ordered, one element: negligible next to the transform.
+            be.barrier(self.group)
             a = self._fft_then_exchange(x, scratch, r1, n2, 0, forward, None)                          # [n2_loc][n1]
             b = self._fft_then_exchange(a, x, r2, n1, n1, forward, (forward, self.rank * r2, self.n))  # [k1_loc][n2]
             if not natural_order:

@@ -44,7 +44,12 @@ int fourier_b200_transform_batch_double(FB200_PLAN_D *plan, const void *in, void
                                         int transform);
 
 /* Device pointers only; enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) and NOT
- * synchronised: the call returns as soon as the kernels are queued. */
+ * synchronised: the call returns as soon as the kernels are queued.
+ * Device buffers (here and above) must be 16-byte aligned (cudaMalloc / torch allocations are; a slice that
+ * starts at an odd f32 sample is not): a misaligned pointer is refused with cudaErrorMisalignedAddress.
+ * A plan owns ONE set of scratch buffers and work-queue counters: besides "not two threads at once" (a plan is
+ * Send, not Sync, as in the reference) this means ONE STREAM AT A TIME -- do not enqueue a plan on a second
+ * stream while a call on another stream is still running; use one plan per stream. */
 int fourier_b200_transform_batch_async_float(FB200_PLAN_F *plan, const void *in_dev, void *out_dev,
                                              size_t batch, int transform, void *cuda_stream);
 int fourier_b200_transform_batch_async_double(FB200_PLAN_D *plan, const void *in_dev, void *out_dev,
@@ -65,6 +70,9 @@ struct fourier_b200_plan_info {
 int fourier_b200_plan_info_float(FB200_PLAN_F *plan, struct fourier_b200_plan_info *out);
 int fourier_b200_plan_info_double(FB200_PLAN_D *plan, struct fourier_b200_plan_info *out);
 const char *fourier_b200_path_name(int path);
+/* Name of the kernel that moves (nearly) all of the plan's bytes, as a profiler lists it. */
+const char *fourier_b200_plan_kernel_float(FB200_PLAN_F *plan);
+const char *fourier_b200_plan_kernel_double(FB200_PLAN_D *plan);
 
 /* Plans restricted to the general one-kernel-per-stage path (testing / comparison). */
 FB200_F *fourier_b200_create_general_float(size_t size);

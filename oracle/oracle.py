@@ -12,6 +12,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libfourier_oracle.so")
+_AVX2_PATH = os.path.join(_HERE, "libfourier_oracle_avx2.so")   # -O3 -mavx2 build, used for TIMING only
 
 FFT, IFFT, UNSCALED_IFFT, SQRT_SCALED_FFT, SQRT_SCALED_IFFT = range(5)
 SEED = 0xDEADBEEF  # echoes fourier/tests/integrity.rs:159
@@ -20,21 +21,36 @@ SEED = 0xDEADBEEF  # echoes fourier/tests/integrity.rs:159
 def build(force=False):
     """Compile the C restatement with the committed Makefile (gcc, -ffp-contract=off)."""
     src = [os.path.join(_HERE, f) for f in ("fourier_oracle.c", "fourier_oracle_impl.inc", "fourier_oracle.h")]
-    if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(s) for s in src)):
+    newest = max(os.path.getmtime(s) for s in src)
+    if not force and all(os.path.exists(p) and os.path.getmtime(p) >= newest for p in (_LIB_PATH, _AVX2_PATH)):
         return _LIB_PATH
     subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
     return _LIB_PATH
 
 
 _lib = None
+_timing_lib = None
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        L = ctypes.CDLL(_LIB_PATH)
+def _cpu_has_avx2():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " avx2" in line
+    except OSError:
+        pass
+    return False
+
+
+def timing_build():
+    """Which build the timing legs run: 'O3 avx2' when the host CPU has AVX2, else the plain 'O2 scalar' one."""
+    return "gcc -O3 -mavx2 -ffp-contract=off" if _cpu_has_avx2() else "gcc -O2 -ffp-contract=off (no AVX2 on this host)"
+
+
+def _bind(path):
+    if True:
+        L = ctypes.CDLL(path)
         for sfx, real in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
             rp = ctypes.POINTER(real)
             g = lambda name: getattr(L, f"fo_{name}_{sfx}")
@@ -58,8 +74,24 @@ def lib():
                                              ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
         L.fo_hash64.restype = ctypes.c_uint64
         L.fo_hash64.argtypes = [ctypes.c_uint64, ctypes.c_uint64]
-        _lib = L
+    return L
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = _bind(_LIB_PATH)
     return _lib
+
+
+def timing_lib():
+    """The AVX2 -O3 build of the same source (bench.py's CPU arm); falls back to lib() on a host without AVX2."""
+    global _timing_lib
+    if _timing_lib is None:
+        build()
+        _timing_lib = _bind(_AVX2_PATH) if _cpu_has_avx2() else lib()
+    return _timing_lib
 
 
 def _sfx(dtype):
@@ -130,14 +162,15 @@ def transform(x, transform=FFT):
         p.close()
 
 
-def transform_batch(x, transform=FFT, threads=1):
-    """Multi-threaded batch (one plan per thread). Returns (out, seconds of the transform loops)."""
+def transform_batch(x, transform=FFT, threads=1, timing=False):
+    """Multi-threaded batch (one plan per thread). Returns (out, seconds of the transform loops).
+    timing=True runs the AVX2 -O3 build (timing_lib) instead of the plain one the parity tests use."""
     x = np.ascontiguousarray(x)
     n = x.shape[-1]
     batch = x.size // n
     out = np.empty_like(x)
     sec = ctypes.c_double(0.0)
-    rc = getattr(lib(), f"fo_transform_batch_{_sfx(x.dtype)}")(
+    rc = getattr(timing_lib() if timing else lib(), f"fo_transform_batch_{_sfx(x.dtype)}")(
         n, x.ctypes.data, out.ctypes.data, batch, int(transform), int(threads), ctypes.byref(sec))
     if rc != 0:
         raise RuntimeError("oracle batch transform failed")

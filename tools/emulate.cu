@@ -310,7 +310,9 @@ static int check_fused(const char* name, double tol) {
     printf("  per warp: %.1f lines of 128 B per pass-1 store instruction (%d B stored), %.1f different pass-2 stage twiddles\n",
            (double)lines / (GT / 32), 32 * (int)sizeof(V), (double)twiddles / (GT / 32));
   }
-  auto twa = make_twa<T>(R, R);
+  auto twa_pairs = make_twa<T>(R, R);
+  std::vector<TwPair<T>> twa(twa_pairs.size());     // the kernel re-lays the table out in 8-byte planes
+  for (int i = 0; i < (int)twa_pairs.size(); ++i) fused::FusedMath<Cfg, true>::relayout_twa(twa.data(), twa_pairs.data(), i);
   std::vector<V> tbase, tstep;
   make_factored_twiddles<T>((size_t)N, (size_t)N2, R, C, tbase, tstep, true);
   int bad = 0;
