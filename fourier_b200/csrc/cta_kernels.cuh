@@ -1,0 +1,211 @@
+// cta_kernels.cuh -- one CTA owns whole transforms in shared memory: the Stockham autosort stage loop of the
+// reference (fourier-algorithms/src/autosort/mod.rs:211-284,313-404: read (k*m+i)*stride+j, DFT_R, post-twiddle
+// w_S^{i*k}, write (i*R+k)*stride+j, ping-pong between two buffers) with ALL stages inside one kernel:
+// the first stage reads global memory, the last one writes it, everything in between stays in shared memory.
+// HBM sees each sample once in and once out, whatever the number of stages.
+//
+// Serves every size the register-tile kernels do not: {2,3}-smooth N that are not a power of two (radix-3 is a
+// first-class stage of the reference: mod.rs:20-21, butterfly.rs:9-22; its benches run 243 / 729 / 2187), powers of
+// two between the on-chip and the two-pass kernels, and -- CHIRP mode -- the reference's Bluestein chirp-z
+// (bluesteins.rs:218-259) for inner sizes M above the warp-level fused kernel: x*chirp (zero-padded to M) -> FFT_M
+// -> *W -> IFFT_M -> *chirp*scale, the two pointwise products folded into the first loads of the two transforms and
+// the last into the final store; the padded length-M intermediates never leave the SM.
+//
+// Layout: a group of `group` transforms of length `len` lives in a buffer of group*len samples, element e at word
+// e + (e >> 5) (one pad element per 32: the scattered writes (i*R+k)*stride+j of the early stages, stride < 32,
+// then spread over all banks -- checked by tools/emulate.cu).  One thread = one radix-R butterfly at a time;
+// consecutive threads take consecutive q = i*stride + j, so shared-memory reads and the global loads / stores of
+// the first / last stage are contiguous.
+//
+// Every function is __host__ __device__: tools/emulate.cu runs the same code thread by thread on the CPU.
+#pragma once
+
+#include "cplx.cuh"
+
+namespace fb200 {
+namespace cta {
+
+constexpr int kMaxStages = 16;
+constexpr int kThreads = 256;
+
+struct Stages {
+  int count;
+  int radix[kMaxStages];
+};
+
+FB_HD int padded(int e) { return e + (e >> 5); }
+
+// Radix-9 butterfly, natural order in and out: 3 x 3 Cooley-Tukey on radix-3 butterflies.
+template <bool FWD, typename T> FB_HD void dft9(cpx<T> (&x)[9]) {
+  // n = 3*n1 + n2, k = k1 + 3*k2;  w_9^1, w_9^2, w_9^4 (forward = exp(-2 pi i k / 9))
+  constexpr T c1 = (T)0.76604444311897803520239265055542, s1 = (T)0.64278760968653932632264340990726;
+  constexpr T c2 = (T)0.17364817766693034885171662676931, s2 = (T)0.98480775301220805936674302458952;
+  constexpr T c4 = (T)-0.93969262078590838405410927732473, s4 = (T)0.34202014332566873304409961468226;
+  cpx<T> a[3][3];
+#pragma unroll
+  for (int n2 = 0; n2 < 3; ++n2) {
+    cpx<T> t[3] = {x[n2], x[3 + n2], x[6 + n2]};
+    dft3<FWD, T>(t);
+    a[n2][0] = t[0]; a[n2][1] = t[1]; a[n2][2] = t[2];
+  }
+  const T sg = FWD ? (T)-1 : (T)1;
+  a[1][1] = cmul(a[1][1], mk<T>(c1, sg * s1));
+  a[1][2] = cmul(a[1][2], mk<T>(c2, sg * s2));
+  a[2][1] = cmul(a[2][1], mk<T>(c2, sg * s2));
+  a[2][2] = cmul(a[2][2], mk<T>(c4, sg * s4));
+#pragma unroll
+  for (int k1 = 0; k1 < 3; ++k1) {
+    cpx<T> t[3] = {a[0][k1], a[1][k1], a[2][k1]};
+    dft3<FWD, T>(t);
+    x[k1] = t[0]; x[k1 + 3] = t[1]; x[k1 + 6] = t[2];
+  }
+}
+
+// DFT of R register values, natural order in and out; R in {2, 3, 4, 8, 9, 16}.
+template <int R, bool FWD, typename T> FB_HD void dft_natural(cpx<T> (&x)[R]) {
+  if constexpr (R == 3) {
+    dft3<FWD, T>(x);
+  } else if constexpr (R == 9) {
+    dft9<FWD, T>(x);
+  } else {
+    dft_pow2<R, FWD, T>(x);
+    cpx<T> y[R];
+    static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; y[k] = x[rev<R>(k)]; });
+    static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; x[k] = y[k]; });
+  }
+}
+
+// Where a stage reads from / writes to.
+enum : int {
+  kInGlobal = 0,       // the user's input
+  kInShared = 1,       // the other ping-pong buffer
+  kInGlobalChirp = 2,  // CHIRP: x[e] * chirp[e] for e < n, 0 up to len
+  kInSharedW = 3,      // CHIRP: buffer[e] * W[e]
+};
+enum : int {
+  kOutShared = 0,
+  kOutGlobal = 1,       // the user's output (times scale)
+  kOutGlobalChirp = 2,  // CHIRP: out[e] = v * chirp[e] * scale for e < n
+};
+
+template <typename T> struct Args {
+  const cpx<T>* in;
+  cpx<T>* out;
+  const cpx<T>* wtab;    // w_len^k, k < len, forward
+  const cpx<T>* chirp;   // CHIRP: forward chirp, n entries
+  const cpx<T>* wf;      // CHIRP: W = FFT_len(wrapped conjugate chirp), len entries, forward direction
+  long batch;
+  int n;                 // user transform length
+  int len;               // length of the transforms computed on chip (n, or the Bluestein inner size M)
+  int group;             // transforms per CTA iteration
+  T scale;
+  Stages st;
+};
+
+// One stage of the group's transforms for thread `tid` of `nthreads`: FWD = direction of this FFT's twiddles,
+// DIR = direction of the user's transform (chirp / W conjugation in CHIRP mode).
+template <typename T, int R, bool FWD, bool DIR>
+FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cnt, int sub, int stride, int in_mode,
+                     int out_mode, const cpx<T>* sin, cpx<T>* sout) {
+  using V = cpx<T>;
+  const int per = a.len / R, m = sub / R;
+  const int total = cnt * per;
+  for (int g = tid; g < total; g += nthreads) {
+    const int tl = g / per, q = g - tl * per;
+    const int i = q / stride, j = q - i * stride;
+    const long b = first + tl;
+    V x[R];
+    static_for<0, R>([&](auto K) FB_LAMBDA {
+      constexpr int k = decltype(K)::value;
+      const int e = (k * m + i) * stride + j;
+      if (in_mode == kInShared) {
+        x[k] = sin[padded(tl * a.len + e)];
+      } else if (in_mode == kInGlobal) {
+        x[k] = a.in[b * a.n + e];
+      } else if (in_mode == kInGlobalChirp) {
+        x[k] = e < a.n ? ctw<DIR>(a.in[b * a.n + e], a.chirp[e]) : mk<T>((T)0, (T)0);
+      } else {
+        x[k] = ctw<DIR>(sin[padded(tl * a.len + e)], a.wf[e]);
+      }
+    });
+    dft_natural<R, FWD, T>(x);
+    if (sub != R) {
+      // w_S^{i*k} = w_len^{i*k*stride}; i*k < S, so the index stays below len
+      static_for<1, R>([&](auto K) FB_LAMBDA {
+        constexpr int k = decltype(K)::value;
+        x[k] = ctw<FWD>(x[k], a.wtab[i * k * stride]);
+      });
+    }
+    static_for<0, R>([&](auto K) FB_LAMBDA {
+      constexpr int k = decltype(K)::value;
+      const int e = (i * R + k) * stride + j;
+      if (out_mode == kOutShared) {
+        sout[padded(tl * a.len + e)] = x[k];
+      } else if (out_mode == kOutGlobal) {
+        a.out[b * a.n + e] = cscale(x[k], a.scale);
+      } else if (e < a.n) {
+        a.out[b * a.n + e] = cscale(ctw<DIR>(x[k], a.chirp[e]), a.scale);
+      }
+    });
+  }
+}
+
+template <typename T, bool FWD, bool DIR>
+FB_HD void dispatch_stage(int radix, const Args<T>& a, int tid, int nthreads, long first, int cnt, int sub, int stride,
+                          int in_mode, int out_mode, const cpx<T>* sin, cpx<T>* sout) {
+  switch (radix) {
+    case 2: run_stage<T, 2, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
+    case 3: run_stage<T, 3, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
+    case 4: run_stage<T, 4, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
+    case 8: run_stage<T, 8, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
+    case 9: run_stage<T, 9, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
+    default: run_stage<T, 16, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
+  }
+}
+
+// The stage program of one group, as (transform number, stage) steps separated by CTA barriers.  Plain mode: one
+// FFT in direction DIR.  CHIRP mode: FFT_len forward, then FFT_len inverse.  Step s of `steps()`; the caller puts
+// a barrier between consecutive steps (tools/emulate.cu: a loop over the threads).
+template <typename T, bool DIR, bool CHIRP> struct Program {
+  static FB_HD int steps(const Args<T>& a) { return CHIRP ? 2 * a.st.count : a.st.count; }
+  static FB_HD void step(const Args<T>& a, int s, int tid, int nthreads, long first, int cnt, cpx<T>* buf0, cpx<T>* buf1) {
+    const int nst = a.st.count;
+    const int k = s < nst ? s : s - nst;          // stage within its transform
+    int sub = a.len, stride = 1;
+    for (int q = 0; q < k; ++q) { sub /= a.st.radix[q]; stride *= a.st.radix[q]; }
+    const bool first_stage = k == 0, last_stage = k == nst - 1;
+    const cpx<T>* sin = (s & 1) ? buf0 : buf1;    // step s writes buf[s & 1]
+    cpx<T>* sout = (s & 1) ? buf1 : buf0;
+    if constexpr (!CHIRP) {
+      dispatch_stage<T, DIR, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride,
+                                  first_stage ? kInGlobal : kInShared, last_stage ? kOutGlobal : kOutShared, sin, sout);
+    } else if (s < nst) {
+      dispatch_stage<T, true, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride,
+                                   first_stage ? kInGlobalChirp : kInShared, kOutShared, sin, sout);
+    } else {
+      dispatch_stage<T, false, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride,
+                                    first_stage ? kInSharedW : kInShared, last_stage ? kOutGlobalChirp : kOutShared,
+                                    sin, sout);
+    }
+  }
+};
+
+template <typename T, bool DIR, bool CHIRP>
+__global__ void __launch_bounds__(kThreads)
+cta_fft_kernel(const Args<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cpx<T>* buf0 = reinterpret_cast<cpx<T>*>(smem_raw);
+  cpx<T>* buf1 = buf0 + padded(a.group * a.len) + 1;
+  using P = Program<T, DIR, CHIRP>;
+  const int steps = P::steps(a);
+  for (long first = (long)blockIdx.x * a.group; first < a.batch; first += (long)gridDim.x * a.group) {
+    const int cnt = (int)(a.batch - first < a.group ? a.batch - first : a.group);
+    for (int s = 0; s < steps; ++s) {
+      P::step(a, s, threadIdx.x, kThreads, first, cnt, buf0, buf1);
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace cta
+}  // namespace fb200

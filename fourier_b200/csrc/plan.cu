@@ -39,6 +39,7 @@ const char* path_name(Path p) {
     case Path::kGlobalStages: return "global_stages";
     case Path::kBluestein: return "bluestein";
     case Path::kBluesteinFused: return "bluestein_fused";
+    case Path::kCta: return "onchip_cta";
   }
   return "?";
 }
@@ -145,7 +146,8 @@ const char* Plan<T>::kernel_name() const {
     case Path::kTwoPass: return fused_ops_ ? "fused::fused_twopass_kernel" : "twopass::tile_kernel (pass 1 + pass 2)";
     case Path::kGlobalStages: return "stockham_stage_kernel (one launch per radix stage)";
     case Path::kBluestein: return "chirp / pointwise kernels around the inner plan's kernels";
-    case Path::kBluesteinFused: return "onchip::bluestein_fused_kernel";
+    case Path::kBluesteinFused: return cta_chirp_ ? "cta::cta_fft_kernel (chirp mode)" : "onchip::bluestein_fused_kernel";
+    case Path::kCta: return "cta::cta_fft_kernel";
   }
   return "?";
 }
@@ -172,6 +174,8 @@ cudaError_t Plan<T>::init(size_t n, int device, bool allow_fast_paths) {
       if (init_onchip() == cudaSuccess) { path_ = Path::kOnChip; return cudaSuccess; }
       if (init_twopass() == cudaSuccess) { path_ = Path::kTwoPass; return cudaSuccess; }
     }
+    // everything else that fits two shared-memory buffers: one kernel, one HBM round trip
+    if (allow_fast_paths && init_cta(n) == cudaSuccess) { path_ = Path::kCta; return cudaSuccess; }
     path_ = Path::kGlobalStages;
     return init_global_stages();
   }
@@ -231,6 +235,14 @@ cudaError_t Plan<T>::init_bluestein(bool allow_fast_paths) {
     path_ = Path::kBluesteinFused;
     return cudaSuccess;
   }
+  if (allow_fast_paths && init_cta(m_) == cudaSuccess) {
+    // inner size above the warp-level kernel: the CTA-level kernel in chirp mode, still one launch
+    FB_CHECK(upload<T>(chirp_, chirp));
+    FB_CHECK(upload<T>(wf_, wf));
+    cta_chirp_ = true;
+    path_ = Path::kBluesteinFused;
+    return cudaSuccess;
+  }
   inner_.reset(Plan<T>::create(m_, device_, allow_fast_paths));
   if (!inner_) return cudaErrorUnknown;
   FB_CHECK(upload<T>(chirp_, chirp));
@@ -275,7 +287,9 @@ cudaError_t Plan<T>::exec_device(const C* in, C* out, size_t batch, int code, cu
     case Path::kTwoPass: return exec_twopass(in, out, batch, code, stream);
     case Path::kGlobalStages: return exec_global_stages(in, out, batch, code, stream);
     case Path::kBluestein: return exec_bluestein(in, out, batch, code, stream);
-    case Path::kBluesteinFused: return exec_bluestein_fused(in, out, batch, code, stream);
+    case Path::kBluesteinFused:
+      return cta_chirp_ ? exec_cta(in, out, batch, code, stream, true) : exec_bluestein_fused(in, out, batch, code, stream);
+    case Path::kCta: return exec_cta(in, out, batch, code, stream, false);
   }
   return cudaErrorUnknown;
 }

@@ -26,6 +26,8 @@ enum class Path : int {
   kGlobalStages = 3,    // one kernel per Stockham stage over HBM ({2,3}-smooth N, any size)
   kBluestein = 4,       // chirp-z around a pow2 inner plan, separate kernels
   kBluesteinFused = 5,  // chirp-z with the inner FFTs on chip, one kernel
+  kCta = 6,             // whole transforms in shared memory, one CTA per group of transforms, all Stockham stages
+                        // in one kernel ({2,3}-smooth N, pow2 N between the on-chip and two-pass kernels)
 };
 
 const char* path_name(Path p);
@@ -101,10 +103,12 @@ class Plan {
   cudaError_t exec_twopass(const C* in, C* out, size_t batch, int code, cudaStream_t s);
   cudaError_t exec_bluestein(const C* in, C* out, size_t batch, int code, cudaStream_t s);
   cudaError_t exec_bluestein_fused(const C* in, C* out, size_t batch, int code, cudaStream_t s);
+  cudaError_t exec_cta(const C* in, C* out, size_t batch, int code, cudaStream_t s, bool chirp);
 
   cudaError_t init_global_stages();
   cudaError_t init_onchip();
   cudaError_t init_twopass();
+  cudaError_t init_cta(size_t len);   // len = n_, or the Bluestein inner size
   cudaError_t init_bluestein(bool allow_fast_paths);
   cudaError_t init_bluestein_fused(const std::vector<double>& chirp_re, const std::vector<double>& chirp_im,
                                    const std::vector<double>& w_re, const std::vector<double>& w_im);
@@ -126,6 +130,10 @@ class Plan {
   const void* fused_ops_ = nullptr;  // FusedOps<T>: persistent single-launch variant
   int ring_ = 0, lag_ = 0, sm_count_ = 148;
   DeviceBuffer counters_, tbase_, tstep_, trace_;
+
+  // kCta (and kBluesteinFused through the CTA kernel): on-chip transform length, radices_ and wtab_ as above
+  size_t cta_len_ = 0;
+  bool cta_chirp_ = false;
 
   // kBluestein*: chirp x[i] (N entries), W = FFT_M(wrapped chirp) (M entries), both forward;
   // the inverse direction uses their conjugate-symmetric counterparts computed at plan time.

@@ -58,7 +58,7 @@ int fourier_b200_transform_batch_async_double(FB200_PLAN_D *plan, const void *in
 /* Plan introspection (Fft::size, fourier-algorithms/src/fft.rs:45, and the chosen strategy). */
 struct fourier_b200_plan_info {
   size_t size;        /* transform length N */
-  int path;           /* 0 trivial, 1 onchip, 2 twopass, 3 global_stages, 4 bluestein, 5 bluestein_fused */
+  int path;           /* 0 trivial, 1 onchip, 2 twopass, 3 global_stages, 4 bluestein, 5 bluestein_fused, 6 onchip_cta */
   size_t inner_size;  /* Bluestein inner length next_pow2(2N-1) (bluesteins.rs:110), else 0 */
   int inner_path;
   size_t n1, n2;      /* two-pass split N = n1*n2, else 0 */
