@@ -81,18 +81,9 @@ template <typename T>
 cudaError_t Plan<T>::init_cta(size_t len) {
   if (!is_23_smooth(len) || !cta_fits<T>(len)) return cudaErrorNotSupported;
   cta_len_ = len;
-  size_t r = len;
-  int twos = 0, threes = 0;
-  while (r % 2 == 0) { r /= 2; ++twos; }
-  while (r % 3 == 0) { r /= 3; ++threes; }
-  radices_.clear();
-  while (twos >= 4) { radices_.push_back(16); twos -= 4; }
-  if (twos == 3) radices_.push_back(8);
-  if (twos == 2) radices_.push_back(4);
-  if (twos == 1) radices_.push_back(2);
-  while (threes >= 2) { radices_.push_back(9); threes -= 2; }
-  if (threes == 1) radices_.push_back(3);
-  if (radices_.size() > (size_t)cta::kMaxStages) return cudaErrorNotSupported;
+  cta::Stages st;
+  if (!cta::factorize(len, st)) return cudaErrorNotSupported;
+  radices_.assign(st.radix, st.radix + st.count);
   std::vector<cpx<T>> w(len);
   for (size_t k = 0; k < len; ++k) {
     double re, im;

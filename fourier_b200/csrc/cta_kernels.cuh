@@ -35,6 +35,27 @@ struct Stages {
 
 FB_HD int padded(int e) { return e + (e >> 5); }
 
+// Stage radices of a {2,3}-smooth length: 16s, then one of 8 / 4 / 2, then 9s, then a 3 (the reference factors
+// [4, 8.., 4.., 3.., 2..], autosort/mod.rs:104-117; wider butterflies = fewer sweeps over shared memory).
+// Returns false when len is not {2,3}-smooth or needs more than kMaxStages stages.
+inline bool factorize(size_t len, Stages& st) {
+  st.count = 0;
+  for (int i = 0; i < kMaxStages; ++i) st.radix[i] = 0;
+  if (len < 2) return false;
+  int twos = 0, threes = 0;
+  while (len % 2 == 0) { len /= 2; ++twos; }
+  while (len % 3 == 0) { len /= 3; ++threes; }
+  if (len != 1) return false;
+  auto push = [&](int r) { if (st.count < kMaxStages) st.radix[st.count] = r; ++st.count; };
+  while (twos >= 4) { push(16); twos -= 4; }
+  if (twos == 3) push(8);
+  if (twos == 2) push(4);
+  if (twos == 1) push(2);
+  while (threes >= 2) { push(9); threes -= 2; }
+  if (threes == 1) push(3);
+  return st.count <= kMaxStages;
+}
+
 // Radix-9 butterfly, natural order in and out: 3 x 3 Cooley-Tukey on radix-3 butterflies.
 template <bool FWD, typename T> FB_HD void dft9(cpx<T> (&x)[9]) {
   // n = 3*n1 + n2, k = k1 + 3*k2;  w_9^1, w_9^2, w_9^4 (forward = exp(-2 pi i k / 9))

@@ -138,7 +138,50 @@ def test_random_sizes_all_paths(real):
             assert e < TOL[real], (n, code, p.info()["path_name"], e)
         p.close()
     print(real, "paths exercised:", seen)
-    assert {"global_stages", "bluestein", "bluestein_fused"} <= set(seen)
+    assert {"global_stages", "bluestein", "bluestein_fused", "onchip_cta"} <= set(seen)
+
+
+def test_smooth_sizes_run_in_one_launch():
+    """No {2,3}-smooth N <= 4096 falls to the one-kernel-per-stage path, and the reference's own bench sizes
+    (fourier-bench/benches/fft_bench.rs:153-159: 243/729/2187 radix-3, 1418/3125/1013 Bluestein) are ONE launch."""
+    n = 2
+    smooth = []
+    for a in range(13):
+        for b in range(8):
+            v = (2 ** a) * (3 ** b)
+            if 2 <= v <= 4096:
+                smooth.append(v)
+    for real in ("f32", "f64"):
+        for v in sorted(smooth):
+            p = create(real, v)
+            assert p.info()["path_name"] != "global_stages", (real, v, p.info()["path_name"])
+            p.close()
+        for v in (243, 729, 2187, 96, 384, 1536, 1418, 3125, 1013, 222, 722):
+            x = O.fill_input(5, v, NP[real], first_transform=3)
+            p = create(real, v)
+            for code in (T.Fft, T.Ifft, T.SqrtScaledFft):
+                got = gpu_transform(p, x, code)
+                assert rel_err(got, O.transform(x, int(code))) < TOL[real], (real, v, code, p.info()["path_name"])
+            assert p.info()["last_launches"] == 1, (real, v, p.info()["path_name"], p.info()["last_launches"])
+            p.close()
+
+
+@pytest.mark.parametrize("real", ["f32", "f64"])
+def test_cta_kernel_batches_and_in_place(real):
+    """The CTA-level kernel with batches that are not a multiple of its group size, in place and out of place."""
+    import torch
+    for n in (6, 9, 48, 243, 2187, 3000 if real == "f32" else 1500, 4374, 12288 if real == "f32" else 6144):
+        p = create(real, n)
+        if n not in (3000, 1500):
+            assert p.info()["path_name"] == "onchip_cta", (n, p.info()["path_name"])
+        for batch in (1, 7, 100):
+            x = O.fill_input(batch, n, NP[real], first_transform=batch)
+            want = O.transform(x, O.FFT)
+            assert rel_err(gpu_transform(p, x, T.Fft), want) < TOL[real], (n, batch)
+            d = torch.from_numpy(x.copy()).cuda()
+            p.transform_in_place(d, T.Fft)
+            assert rel_err(d.cpu().numpy(), want) < TOL[real], (n, batch, "in place")
+        p.close()
 
 
 def test_config1_single_1024_via_reference_abi():

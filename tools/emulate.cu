@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <vector>
 
+#include "cta_kernels.cuh"
 #include "fused_kernels.cuh"
 #include "onchip_kernels.cuh"
 #include "twopass_kernels.cuh"
@@ -401,8 +402,113 @@ static int check_queue() {
   return bad;
 }
 
+// ---- CTA-level shared-memory Stockham kernel (cta_kernels.cuh): every step for every thread, barrier = loop end ----
+template <typename T>
+static int check_cta(const char* name, int n, bool chirp_mode, double tol) {
+  using V = cpx<T>;
+  int len = n;
+  if (chirp_mode) { len = 1; while (len < 2 * n - 1) len *= 2; }
+  cta::Args<T> a;
+  if (!cta::factorize((size_t)len, a.st)) { printf("%s N=%d: cannot factorize\n", name, n); return 1; }
+  const int group = std::max(1, (int)(32768 / sizeof(V)) / len), batch = group + 1;   // a full and a partial group
+  std::vector<V> wtab(len), chirp(n), wf(len), x((size_t)batch * n), out((size_t)batch * n);
+  for (int k = 0; k < len; ++k) { double re, im; host_twiddle(k, len, &re, &im); wtab[k] = mk<T>((T)re, (T)im); }
+  if (chirp_mode) {
+    std::vector<double> wr(len, 0.0), wi(len, 0.0);
+    for (int i = 0; i < n; ++i) {
+      double re, im;
+      host_twiddle((size_t)(((unsigned long long)i * i) % (2ull * n)), 2 * (size_t)n, &re, &im);
+      chirp[i] = mk<T>((T)re, (T)im);
+      wr[i] = re; wi[i] = -im;
+      if (i) { wr[len - i] = re; wi[len - i] = -im; }
+    }
+    host_fft_pow2(wr, wi, false);
+    for (int i = 0; i < len; ++i) wf[i] = mk<T>((T)wr[i], (T)wi[i]);
+  }
+  fill<T>(x, 77 + n);
+  a.in = x.data(); a.out = out.data(); a.wtab = wtab.data(); a.chirp = chirp.data(); a.wf = wf.data();
+  a.batch = batch; a.n = n; a.len = len; a.group = group;
+  printf("%s N=%d%s: on-chip length %d, stages", name, n, chirp_mode ? " (chirp-z)" : "", len);
+  for (int i = 0; i < a.st.count; ++i) printf(" %d", a.st.radix[i]);
+  printf(", %d transforms per CTA iteration\n", group);
+  // bank conflicts of the shared-memory accesses, worst warp-wide instruction per stage
+  {
+    int sub = len, stride = 1;
+    for (int sidx = 0; sidx < a.st.count; ++sidx) {
+      const int R = a.st.radix[sidx], per = len / R, m = sub / R;
+      int worst_r = 1, worst_w = 1;
+      for (int warp = 0; warp < std::min(cta::kThreads, group * per) / 32; ++warp)
+        for (int k = 0; k < R; ++k) {
+          std::vector<long> ri, wi2;
+          for (int l = 0; l < 32; ++l) {
+            const int g = warp * 32 + l, tl = g / per, q = g - tl * per, i = q / stride, j = q - i * stride;
+            ri.push_back(cta::padded(tl * len + (k * m + i) * stride + j));
+            wi2.push_back(cta::padded(tl * len + (i * R + k) * stride + j));
+          }
+          worst_r = std::max(worst_r, conflict_degree<(int)sizeof(V)>(ri));
+          worst_w = std::max(worst_w, conflict_degree<(int)sizeof(V)>(wi2));
+        }
+      printf("  stage %d (radix %2d, stride %5d): shared read conflicts x%d, write x%d\n", sidx, R, stride, worst_r, worst_w);
+      sub /= R; stride *= R;
+    }
+  }
+  int bad = 0;
+  std::vector<V> buf0((size_t)cta::padded(group * len) + 1), buf1(buf0.size());
+  for (int dir = 1; dir >= 0; --dir) {
+    a.scale = (T)(chirp_mode ? 0.5 / len : 0.5);
+    for (long first = 0; first < batch; first += group) {
+      const int cnt = (int)std::min<long>(group, batch - first);
+      auto run = [&](auto D, auto Cm) {
+        using P = cta::Program<T, decltype(D)::value, decltype(Cm)::value>;
+        for (int st = 0; st < P::steps(a); ++st)
+          for (int tid = 0; tid < cta::kThreads; ++tid) P::step(a, st, tid, cta::kThreads, first, cnt, buf0.data(), buf1.data());
+      };
+      if (dir && chirp_mode) run(std::true_type{}, std::true_type{});
+      else if (dir) run(std::true_type{}, std::false_type{});
+      else if (chirp_mode) run(std::false_type{}, std::true_type{});
+      else run(std::false_type{}, std::false_type{});
+    }
+    double worst = 0;
+    for (int b = 0; b < batch; ++b) {
+      double me = 0, mr = 0;
+      for (int k = 0; k < n; ++k) {
+        double sr = 0, si = 0;
+        for (int j = 0; j < n; ++j) {
+          double re, im;
+          host_twiddle((size_t)(((unsigned long long)j * k) % n), (size_t)n, &re, &im);
+          if (!dir) im = -im;
+          const double xr = x[(size_t)b * n + j].x, xi = x[(size_t)b * n + j].y;
+          sr += xr * re - xi * im; si += xr * im + xi * re;
+        }
+        sr *= 0.5; si *= 0.5;
+        me = std::max(me, std::hypot(out[(size_t)b * n + k].x - sr, out[(size_t)b * n + k].y - si));
+        mr = std::max(mr, std::hypot(sr, si));
+      }
+      worst = std::max(worst, me / mr);
+    }
+    printf("  %s: max rel err vs naive f64 DFT %.3e %s\n", dir ? "forward" : "inverse", worst, worst < tol ? "OK" : "FAIL");
+    bad += !(worst < tol);
+  }
+  return bad;
+}
+
 int main() {
   int bad = 0;
+  bad += check_cta<float>("cta f32", 243, false, 2e-6);
+  bad += check_cta<float>("cta f32", 729, false, 2e-6);
+  bad += check_cta<float>("cta f32", 2187, false, 3e-6);
+  bad += check_cta<float>("cta f32", 96, false, 2e-6);
+  bad += check_cta<float>("cta f32", 1536, false, 2e-6);
+  bad += check_cta<float>("cta f32", 2048, false, 2e-6);
+  bad += check_cta<float>("cta f32", 6, false, 2e-6);
+  bad += check_cta<float>("cta f32", 9, false, 2e-6);
+  bad += check_cta<double>("cta f64", 768, false, 5e-15);
+  bad += check_cta<double>("cta f64", 81, false, 5e-15);
+  bad += check_cta<double>("cta f64", 1458, false, 5e-15);
+  bad += check_cta<float>("cta f32", 1418, true, 3e-6);
+  bad += check_cta<float>("cta f32", 3125, true, 4e-6);
+  bad += check_cta<double>("cta f64", 1009, true, 1e-13);
+  bad += check_cta<double>("cta f64", 5, true, 1e-13);
   bad += check<float, TwoPass<float, 32, 32, 8, 8, 8, 2, 2>>("f32 2^20 (C=8)", 2e-6);
   bad += check<float, TwoPass<float, 32, 32, 16, 16, 0, 1, 1>>("f32 2^20 (C=16)", 2e-6);
   bad += check<float, TwoPass<float, 16, 16, 16, 16, 0, 2, 2>>("f32 2^16", 2e-6);
