@@ -27,10 +27,26 @@ template <typename T> size_t smem_bytes(int group, int len) {
   return 2 * ((size_t)cta::padded(group * len) + 1) * sizeof(cpx<T>);
 }
 
-// transforms per CTA iteration: about 32 KB per buffer, so that three CTAs share an SM
+// Transforms per CTA iteration: at most about 32 KB per buffer (three CTAs share an SM), and among the candidates
+// the one whose stages leave the fewest of the 256 threads idle in their last round of butterflies.
 template <typename T> int group_for(int len) {
   const int target = (int)(32768 / sizeof(cpx<T>));
-  return std::max(1, target / len);
+  const int gmax = std::max(1, target / len);
+  cta::Stages st;
+  if (!cta::factorize((size_t)len, st)) return gmax;
+  int best = gmax;
+  double best_eff = 0;
+  for (int g = gmax; g >= std::max(1, gmax / 2); --g) {
+    double work = 0, slots = 0;
+    for (int s = 0; s < st.count; ++s) {
+      const double n = (double)g * (len / st.radix[s]);
+      work += n * st.radix[s];
+      slots += std::ceil(n / cta::kThreads) * cta::kThreads * st.radix[s];
+    }
+    const double eff = work / slots;
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = g; }
+  }
+  return best;
 }
 
 template <typename T, bool DIR, bool CHIRP>
@@ -84,13 +100,7 @@ cudaError_t Plan<T>::init_cta(size_t len) {
   cta::Stages st;
   if (!cta::factorize(len, st)) return cudaErrorNotSupported;
   radices_.assign(st.radix, st.radix + st.count);
-  std::vector<cpx<T>> w(len);
-  for (size_t k = 0; k < len; ++k) {
-    double re, im;
-    host_twiddle(k, len, &re, &im);
-    w[k] = mk<T>((T)re, (T)im);
-  }
-  FB_CHECK(upload<T>(wtab_, w));
+  FB_CHECK(upload<T>(wtab_, cta::make_stage_twiddles<T>(len, st, host_twiddle)));
   sm_count_ = sm_count();
   return cudaSuccess;
 }
@@ -112,8 +122,7 @@ cudaError_t Plan<T>::exec_cta(const C* in, C* out, size_t batch, int code, cudaS
   else if (code == kSqrtScaledFft || code == kSqrtScaledIfft) scale = (T)1 / std::sqrt((T)n_);
   if (chirp) scale /= (T)cta_len_;      // the unscaled inner inverse transform
   a.scale = scale;
-  a.st.count = (int)radices_.size();
-  for (int i = 0; i < cta::kMaxStages; ++i) a.st.radix[i] = i < a.st.count ? radices_[i] : 0;
+  cta::factorize(cta_len_, a.st);
   cudaError_t e;
   if (chirp) e = fwd ? launch<T, true, true>(a, sm_count_, s) : launch<T, false, true>(a, sm_count_, s);
   else e = fwd ? launch<T, true, false>(a, sm_count_, s) : launch<T, false, false>(a, sm_count_, s);

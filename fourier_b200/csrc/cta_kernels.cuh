@@ -20,6 +20,8 @@
 // Every function is __host__ __device__: tools/emulate.cu runs the same code thread by thread on the CPU.
 #pragma once
 
+#include <vector>
+
 #include "cplx.cuh"
 
 namespace fb200 {
@@ -31,7 +33,23 @@ constexpr int kThreads = 256;
 struct Stages {
   int count;
   int radix[kMaxStages];
+  int tw_off[kMaxStages];        // first entry of the stage's twiddle block in Args::wtab
+  unsigned magic[kMaxStages];    // ceil(2^32 / stride): q / stride == (q * magic) >> 32 for q * stride < 2^32
 };
+
+// Twiddles of stage s (sub-size S = R*m): block [k-1][i] = w_S^{i*k}, k = 1..R-1, i < m -- transposed so that the
+// threads of a warp (consecutive q = i*stride + j: `stride` lanes share one i, then the next i) read one or two
+// contiguous runs per k; the reference's per-stage layout is [i][k] (autosort/mod.rs:24-46), which a warp would
+// gather with up to 32 different cache lines per load.  The last stage (S == R) has no twiddles.
+inline int twiddle_entries(size_t len, const Stages& st) {
+  size_t sub = len, total = 0;
+  for (int s = 0; s < st.count; ++s) {
+    const size_t r = (size_t)st.radix[s];
+    if (sub != r) total += (r - 1) * (sub / r);
+    sub /= r;
+  }
+  return (int)total;
+}
 
 FB_HD int padded(int e) { return e + (e >> 5); }
 
@@ -46,6 +64,7 @@ inline bool factorize(size_t len, Stages& st) {
   while (len % 2 == 0) { len /= 2; ++twos; }
   while (len % 3 == 0) { len /= 3; ++threes; }
   if (len != 1) return false;
+  const size_t full = ((size_t)1 << twos) * [&] { size_t p = 1; for (int i = 0; i < threes; ++i) p *= 3; return p; }();
   auto push = [&](int r) { if (st.count < kMaxStages) st.radix[st.count] = r; ++st.count; };
   while (twos >= 4) { push(16); twos -= 4; }
   if (twos == 3) push(8);
@@ -53,7 +72,37 @@ inline bool factorize(size_t len, Stages& st) {
   if (twos == 1) push(2);
   while (threes >= 2) { push(9); threes -= 2; }
   if (threes == 1) push(3);
-  return st.count <= kMaxStages;
+  if (st.count > kMaxStages) return false;
+  size_t sub = full, stride = 1;
+  int off = 0;
+  for (int s = 0; s < st.count; ++s) {
+    const size_t r = (size_t)st.radix[s];
+    st.tw_off[s] = off;
+    st.magic[s] = stride == 1 ? 0u : (unsigned)((((unsigned long long)1 << 32) + stride - 1) / stride);
+    if (sub != r) off += (int)((r - 1) * (sub / r));
+    sub /= r;
+    stride *= r;
+  }
+  return true;
+}
+
+// Host side: the twiddle blocks of every stage, `tw(idx, size, &re, &im)` = exp(-2 pi i idx / size) in double.
+template <typename T, class TW>
+inline std::vector<cpx<T>> make_stage_twiddles(size_t len, const Stages& st, TW&& tw) {
+  std::vector<cpx<T>> out((size_t)twiddle_entries(len, st));
+  size_t sub = len;
+  for (int s = 0; s < st.count; ++s) {
+    const size_t r = (size_t)st.radix[s], m = sub / r;
+    if (sub != r)
+      for (size_t k = 1; k < r; ++k)
+        for (size_t i = 0; i < m; ++i) {
+          double re, im;
+          tw(i * k, sub, &re, &im);
+          out[(size_t)st.tw_off[s] + (k - 1) * m + i] = mk<T>((T)re, (T)im);
+        }
+    sub /= r;
+  }
+  return out;
 }
 
 // Radix-9 butterfly, natural order in and out: 3 x 3 Cooley-Tukey on radix-3 butterflies.
@@ -112,7 +161,7 @@ enum : int {
 template <typename T> struct Args {
   const cpx<T>* in;
   cpx<T>* out;
-  const cpx<T>* wtab;    // w_len^k, k < len, forward
+  const cpx<T>* wtab;    // per-stage twiddle blocks (Stages::tw_off, twiddle_entries), forward
   const cpx<T>* chirp;   // CHIRP: forward chirp, n entries
   const cpx<T>* wf;      // CHIRP: W = FFT_len(wrapped conjugate chirp), len entries, forward direction
   long batch;
@@ -124,16 +173,18 @@ template <typename T> struct Args {
 };
 
 // One stage of the group's transforms for thread `tid` of `nthreads`: FWD = direction of this FFT's twiddles,
-// DIR = direction of the user's transform (chirp / W conjugation in CHIRP mode).
+// DIR = direction of the user's transform (chirp / W conjugation in CHIRP mode).  `tw` = the stage's twiddle block.
 template <typename T, int R, bool FWD, bool DIR>
-FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cnt, int sub, int stride, int in_mode,
-                     int out_mode, const cpx<T>* sin, cpx<T>* sout) {
+FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cnt, int sub, int stride, unsigned magic,
+                     const cpx<T>* tw, int in_mode, int out_mode, const cpx<T>* sin, cpx<T>* sout) {
   using V = cpx<T>;
   const int per = a.len / R, m = sub / R;
-  const int total = cnt * per;
-  for (int g = tid; g < total; g += nthreads) {
-    const int tl = g / per, q = g - tl * per;
-    const int i = q / stride, j = q - i * stride;
+  // butterflies of the whole group, transform-major: g = tl * per + q (tl and q advance without a division)
+  int tl = tid / per, q = tid - tl * per;
+  const int dtl = nthreads / per, dq = nthreads - dtl * per;
+  for (; tl < cnt; ) {
+    const int i = stride == 1 ? q : (int)(((unsigned long long)(unsigned)q * magic) >> 32);
+    const int j = q - i * stride;
     const long b = first + tl;
     V x[R];
     static_for<0, R>([&](auto K) FB_LAMBDA {
@@ -151,10 +202,9 @@ FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cn
     });
     dft_natural<R, FWD, T>(x);
     if (sub != R) {
-      // w_S^{i*k} = w_len^{i*k*stride}; i*k < S, so the index stays below len
       static_for<1, R>([&](auto K) FB_LAMBDA {
         constexpr int k = decltype(K)::value;
-        x[k] = ctw<FWD>(x[k], a.wtab[i * k * stride]);
+        x[k] = ctw<FWD>(x[k], tw[(k - 1) * m + i]);      // w_S^{i*k}
       });
     }
     static_for<0, R>([&](auto K) FB_LAMBDA {
@@ -168,20 +218,24 @@ FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cn
         a.out[b * a.n + e] = cscale(ctw<DIR>(x[k], a.chirp[e]), a.scale);
       }
     });
+    tl += dtl; q += dq;
+    if (q >= per) { q -= per; ++tl; }
   }
 }
 
 template <typename T, bool FWD, bool DIR>
 FB_HD void dispatch_stage(int radix, const Args<T>& a, int tid, int nthreads, long first, int cnt, int sub, int stride,
-                          int in_mode, int out_mode, const cpx<T>* sin, cpx<T>* sout) {
+                          unsigned magic, const cpx<T>* tw, int in_mode, int out_mode, const cpx<T>* sin, cpx<T>* sout) {
+#define FB_CTA_STAGE(R) run_stage<T, R, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, magic, tw, in_mode, out_mode, sin, sout)
   switch (radix) {
-    case 2: run_stage<T, 2, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
-    case 3: run_stage<T, 3, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
-    case 4: run_stage<T, 4, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
-    case 8: run_stage<T, 8, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
-    case 9: run_stage<T, 9, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
-    default: run_stage<T, 16, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, in_mode, out_mode, sin, sout); break;
+    case 2: FB_CTA_STAGE(2); break;
+    case 3: FB_CTA_STAGE(3); break;
+    case 4: FB_CTA_STAGE(4); break;
+    case 8: FB_CTA_STAGE(8); break;
+    case 9: FB_CTA_STAGE(9); break;
+    default: FB_CTA_STAGE(16); break;
   }
+#undef FB_CTA_STAGE
 }
 
 // The stage program of one group, as (transform number, stage) steps separated by CTA barriers.  Plain mode: one
@@ -195,16 +249,18 @@ template <typename T, bool DIR, bool CHIRP> struct Program {
     int sub = a.len, stride = 1;
     for (int q = 0; q < k; ++q) { sub /= a.st.radix[q]; stride *= a.st.radix[q]; }
     const bool first_stage = k == 0, last_stage = k == nst - 1;
+    const unsigned magic = a.st.magic[k];
+    const cpx<T>* tw = a.wtab + a.st.tw_off[k];
     const cpx<T>* sin = (s & 1) ? buf0 : buf1;    // step s writes buf[s & 1]
     cpx<T>* sout = (s & 1) ? buf1 : buf0;
     if constexpr (!CHIRP) {
-      dispatch_stage<T, DIR, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride,
+      dispatch_stage<T, DIR, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride, magic, tw,
                                   first_stage ? kInGlobal : kInShared, last_stage ? kOutGlobal : kOutShared, sin, sout);
     } else if (s < nst) {
-      dispatch_stage<T, true, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride,
+      dispatch_stage<T, true, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride, magic, tw,
                                    first_stage ? kInGlobalChirp : kInShared, kOutShared, sin, sout);
     } else {
-      dispatch_stage<T, false, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride,
+      dispatch_stage<T, false, DIR>(a.st.radix[k], a, tid, nthreads, first, cnt, sub, stride, magic, tw,
                                     first_stage ? kInSharedW : kInShared, last_stage ? kOutGlobalChirp : kOutShared,
                                     sin, sout);
     }

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <exception>
 
@@ -172,7 +173,10 @@ cudaError_t Plan<T>::init(size_t n, int device, bool allow_fast_paths) {
     const bool pow2 = (n & (n - 1)) == 0;
     if (allow_fast_paths && pow2) {
       if (init_onchip() == cudaSuccess) { path_ = Path::kOnChip; return cudaSuccess; }
-      if (init_twopass() == cudaSuccess) { path_ = Path::kTwoPass; return cudaSuccess; }
+      // FOURIER_B200_TWOPASS=0 (experiment knob): skip the two-pass kernels, so that sizes the CTA kernel also
+      // covers can be measured on it
+      const char* tp = std::getenv("FOURIER_B200_TWOPASS");
+      if (!(tp && atoi(tp) == 0) && init_twopass() == cudaSuccess) { path_ = Path::kTwoPass; return cudaSuccess; }
     }
     // everything else that fits two shared-memory buffers: one kernel, one HBM round trip
     if (allow_fast_paths && init_cta(n) == cudaSuccess) { path_ = Path::kCta; return cudaSuccess; }

@@ -16,6 +16,9 @@
 #include "onchip_kernels.cuh"
 #include "twopass_kernels.cuh"
 
+#ifndef FB_PAD16
+#define FB_PAD16 8
+#endif
 using namespace fb200;
 using namespace fb200::twopass;
 
@@ -411,8 +414,8 @@ static int check_cta(const char* name, int n, bool chirp_mode, double tol) {
   cta::Args<T> a;
   if (!cta::factorize((size_t)len, a.st)) { printf("%s N=%d: cannot factorize\n", name, n); return 1; }
   const int group = std::max(1, (int)(32768 / sizeof(V)) / len), batch = group + 1;   // a full and a partial group
-  std::vector<V> wtab(len), chirp(n), wf(len), x((size_t)batch * n), out((size_t)batch * n);
-  for (int k = 0; k < len; ++k) { double re, im; host_twiddle(k, len, &re, &im); wtab[k] = mk<T>((T)re, (T)im); }
+  std::vector<V> wtab = cta::make_stage_twiddles<T>((size_t)len, a.st, host_twiddle);
+  std::vector<V> chirp(n), wf(len), x((size_t)batch * n), out((size_t)batch * n);
   if (chirp_mode) {
     std::vector<double> wr(len, 0.0), wi(len, 0.0);
     for (int i = 0; i < n; ++i) {
@@ -546,6 +549,8 @@ int main() {
   bad += check_fused<fused::FusedCfg<double, 16, 8, 3, 4, 3>>("fused f64 2^16", 5e-15);
   bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 8, 2, true>>("fused f32 2^20", 2e-6);
   bad += check_fused<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>("fused f64 2^16", 5e-15);
+  bad += check_fused<fused::FusedCfg<float, 16, 8, 4, FB_PAD16, 4, true>>("fused f32 2^16", 2e-6);
+  bad += check_fused<fused::FusedCfg<float, 16, 8, 4, FB_PAD16, 4>>("fused f32 2^16", 2e-6);
   bad += check_queue();
   printf(bad ? "EMULATION FAILED (%d)\n" : "EMULATION OK\n", bad);
   return bad ? 1 : 0;
