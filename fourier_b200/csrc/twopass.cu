@@ -110,6 +110,11 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
     if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 2, true>>::ops(8, 4);
     return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
   }
+  if (n == ((size_t)1 << 16)) {
+    // 256 x 256 with 16 x 16 register tiles: four 128-thread groups (the f64 shape); 64-byte tile rows as at 2^20
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4>>::ops(64, 32);
+    return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true>>::ops(64, 32);
+  }
   return nullptr;
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
