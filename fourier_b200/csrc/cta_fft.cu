@@ -24,7 +24,7 @@ namespace {
 constexpr size_t kSmemLimit = 227 * 1024;
 
 template <typename T> size_t smem_bytes(int group, int len) {
-  return 2 * ((size_t)cta::padded(group * len) + 1) * sizeof(cpx<T>);
+  return 2 * (size_t)cta::buffer_elems(group, len) * sizeof(cpx<T>);
 }
 
 // Transforms per CTA iteration: at most about 32 KB per buffer (three CTAs share an SM), and among the candidates
@@ -56,6 +56,10 @@ cudaError_t launch(const cta::Args<T>& a, int sms, cudaStream_t s) {
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(cta::cta_fft_kernel<T, DIR, CHIRP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemLimit);
+    if (e != cudaSuccess) return e;
+    // several CTAs per SM need the full shared-memory carve-out (the default heuristic left room for two of three)
+    e = cudaFuncSetAttribute(cta::cta_fft_kernel<T, DIR, CHIRP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured = kSmemLimit;
   }
@@ -123,6 +127,7 @@ cudaError_t Plan<T>::exec_cta(const C* in, C* out, size_t batch, int code, cudaS
   if (chirp) scale /= (T)cta_len_;      // the unscaled inner inverse transform
   a.scale = scale;
   cta::factorize(cta_len_, a.st);
+  a.pad = a.st.radix[0] % 2 == 0 ? 1 : 0;
   cudaError_t e;
   if (chirp) e = fwd ? launch<T, true, true>(a, sm_count_, s) : launch<T, false, true>(a, sm_count_, s);
   else e = fwd ? launch<T, true, false>(a, sm_count_, s) : launch<T, false, false>(a, sm_count_, s);

@@ -52,6 +52,7 @@ inline int twiddle_entries(size_t len, const Stages& st) {
 }
 
 FB_HD int padded(int e) { return e + (e >> 5); }
+FB_HD int buffer_elems(int group, int len) { return padded(group * len) + 1; }
 
 // Stage radices of a {2,3}-smooth length: 16s, then one of 8 / 4 / 2, then 9s, then a 3 (the reference factors
 // [4, 8.., 4.., 3.., 2..], autosort/mod.rs:104-117; wider butterflies = fewer sweeps over shared memory).
@@ -168,17 +169,26 @@ template <typename T> struct Args {
   int n;                 // user transform length
   int len;               // length of the transforms computed on chip (n, or the Bluestein inner size M)
   int group;             // transforms per CTA iteration
+  int pad;               // buffers use the padded layout (needed iff the first radix is even)
   T scale;
   Stages st;
 };
 
 // One stage of the group's transforms for thread `tid` of `nthreads`: FWD = direction of this FFT's twiddles,
 // DIR = direction of the user's transform (chirp / W conjugation in CHIRP mode).  `tw` = the stage's twiddle block.
-template <typename T, int R, bool FWD, bool DIR>
+// Index arithmetic (the first version of this kernel issued more integer than floating-point instructions,
+// profiles/r02_cta_kernel_ncu.txt): with per = len / R the R inputs of butterfly q sit at q + k*per and its outputs
+// at w0 + k*stride, w0 = i*R*stride + j -- both linear in k; the pad term e >> 5 is linear too whenever per
+// (stride) is a multiple of 32, and absent when the buffers are not padded at all (PAD = false: first radix odd,
+// whose stride-1 writes are conflict-free as they are).  The source / destination kind is tested once per
+// butterfly, outside the unrolled element loops.
+template <typename T, int R, bool FWD, bool DIR, bool PAD>
 FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cnt, int sub, int stride, unsigned magic,
                      const cpx<T>* tw, int in_mode, int out_mode, const cpx<T>* sin, cpx<T>* sout) {
   using V = cpx<T>;
   const int per = a.len / R, m = sub / R;
+  const bool lin_r = !PAD || (per & 31) == 0, lin_w = !PAD || (stride & 31) == 0;
+  const int dr = PAD ? per + (per >> 5) : per, dw = PAD ? stride + (stride >> 5) : stride;
   // butterflies of the whole group, transform-major: g = tl * per + q (tl and q advance without a division)
   int tl = tid / per, q = tid - tl * per;
   const int dtl = nthreads / per, dq = nthreads - dtl * per;
@@ -187,37 +197,59 @@ FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cn
     const int j = q - i * stride;
     const long b = first + tl;
     V x[R];
-    static_for<0, R>([&](auto K) FB_LAMBDA {
-      constexpr int k = decltype(K)::value;
-      const int e = (k * m + i) * stride + j;
-      if (in_mode == kInShared) {
-        x[k] = sin[padded(tl * a.len + e)];
-      } else if (in_mode == kInGlobal) {
-        x[k] = a.in[b * a.n + e];
-      } else if (in_mode == kInGlobalChirp) {
-        x[k] = e < a.n ? ctw<DIR>(a.in[b * a.n + e], a.chirp[e]) : mk<T>((T)0, (T)0);
+    if (in_mode == kInShared || in_mode == kInSharedW) {
+      const int base = tl * a.len + q;
+      if (lin_r) {
+        const V* p = sin + (PAD ? padded(base) : base);
+        static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; x[k] = p[k * dr]; });
       } else {
-        x[k] = ctw<DIR>(sin[padded(tl * a.len + e)], a.wf[e]);
+        static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; x[k] = sin[padded(base + k * per)]; });
       }
-    });
+      if (in_mode == kInSharedW) {
+        const V* w = a.wf + q;
+        static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; x[k] = ctw<DIR>(x[k], w[k * per]); });
+      }
+    } else {
+      const V* p = a.in + b * a.n + q;
+      if (in_mode == kInGlobal) {
+        static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; x[k] = p[k * per]; });
+      } else {
+        const V* c = a.chirp + q;
+        static_for<0, R>([&](auto K) FB_LAMBDA {
+          constexpr int k = decltype(K)::value;
+          x[k] = q + k * per < a.n ? ctw<DIR>(p[k * per], c[k * per]) : mk<T>((T)0, (T)0);
+        });
+      }
+    }
     dft_natural<R, FWD, T>(x);
     if (sub != R) {
+      const V* t = tw + i;
       static_for<1, R>([&](auto K) FB_LAMBDA {
         constexpr int k = decltype(K)::value;
-        x[k] = ctw<FWD>(x[k], tw[(k - 1) * m + i]);      // w_S^{i*k}
+        x[k] = ctw<FWD>(x[k], t[(k - 1) * m]);      // w_S^{i*k}
       });
     }
-    static_for<0, R>([&](auto K) FB_LAMBDA {
-      constexpr int k = decltype(K)::value;
-      const int e = (i * R + k) * stride + j;
-      if (out_mode == kOutShared) {
-        sout[padded(tl * a.len + e)] = x[k];
-      } else if (out_mode == kOutGlobal) {
-        a.out[b * a.n + e] = cscale(x[k], a.scale);
-      } else if (e < a.n) {
-        a.out[b * a.n + e] = cscale(ctw<DIR>(x[k], a.chirp[e]), a.scale);
+    const int w0 = i * R * stride + j;
+    if (out_mode == kOutShared) {
+      const int base = tl * a.len + w0;
+      if (lin_w) {
+        V* p = sout + (PAD ? padded(base) : base);
+        static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; p[k * dw] = x[k]; });
+      } else {
+        static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; sout[padded(base + k * stride)] = x[k]; });
       }
-    });
+    } else {
+      V* p = a.out + b * a.n + w0;
+      if (out_mode == kOutGlobal) {
+        static_for<0, R>([&](auto K) FB_LAMBDA { constexpr int k = decltype(K)::value; p[k * stride] = cscale(x[k], a.scale); });
+      } else {
+        const V* c = a.chirp + w0;
+        static_for<0, R>([&](auto K) FB_LAMBDA {
+          constexpr int k = decltype(K)::value;
+          if (w0 + k * stride < a.n) p[k * stride] = cscale(ctw<DIR>(x[k], c[k * stride]), a.scale);
+        });
+      }
+    }
     tl += dtl; q += dq;
     if (q >= per) { q -= per; ++tl; }
   }
@@ -226,7 +258,11 @@ FB_HD void run_stage(const Args<T>& a, int tid, int nthreads, long first, int cn
 template <typename T, bool FWD, bool DIR>
 FB_HD void dispatch_stage(int radix, const Args<T>& a, int tid, int nthreads, long first, int cnt, int sub, int stride,
                           unsigned magic, const cpx<T>* tw, int in_mode, int out_mode, const cpx<T>* sin, cpx<T>* sout) {
-#define FB_CTA_STAGE(R) run_stage<T, R, FWD, DIR>(a, tid, nthreads, first, cnt, sub, stride, magic, tw, in_mode, out_mode, sin, sout)
+#define FB_CTA_STAGE(R)                                                                                              \
+  do {                                                                                                             \
+    if (a.pad) run_stage<T, R, FWD, DIR, true>(a, tid, nthreads, first, cnt, sub, stride, magic, tw, in_mode, out_mode, sin, sout);  \
+    else run_stage<T, R, FWD, DIR, false>(a, tid, nthreads, first, cnt, sub, stride, magic, tw, in_mode, out_mode, sin, sout);       \
+  } while (0)
   switch (radix) {
     case 2: FB_CTA_STAGE(2); break;
     case 3: FB_CTA_STAGE(3); break;
@@ -272,7 +308,7 @@ __global__ void __launch_bounds__(kThreads)
 cta_fft_kernel(const Args<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cpx<T>* buf0 = reinterpret_cast<cpx<T>*>(smem_raw);
-  cpx<T>* buf1 = buf0 + padded(a.group * a.len) + 1;
+  cpx<T>* buf1 = buf0 + buffer_elems(a.group, a.len);
   using P = Program<T, DIR, CHIRP>;
   const int steps = P::steps(a);
   for (long first = (long)blockIdx.x * a.group; first < a.batch; first += (long)gridDim.x * a.group) {

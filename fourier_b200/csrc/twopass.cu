@@ -112,8 +112,8 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
   }
   if (n == ((size_t)1 << 16)) {
     // 256 x 256 with 16 x 16 register tiles: four 128-thread groups (the f64 shape); 64-byte tile rows as at 2^20
-    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4>>::ops(64, 32);
-    return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true>>::ops(64, 32);
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4>>::ops(128, 64);
+    return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true>>::ops(128, 64);   // ring 64: 47 %, ring 128: 51 %
   }
   return nullptr;
 }

@@ -430,7 +430,7 @@ static int check_cta(const char* name, int n, bool chirp_mode, double tol) {
   }
   fill<T>(x, 77 + n);
   a.in = x.data(); a.out = out.data(); a.wtab = wtab.data(); a.chirp = chirp.data(); a.wf = wf.data();
-  a.batch = batch; a.n = n; a.len = len; a.group = group;
+  a.batch = batch; a.n = n; a.len = len; a.group = group; a.pad = a.st.radix[0] % 2 == 0 ? 1 : 0;
   printf("%s N=%d%s: on-chip length %d, stages", name, n, chirp_mode ? " (chirp-z)" : "", len);
   for (int i = 0; i < a.st.count; ++i) printf(" %d", a.st.radix[i]);
   printf(", %d transforms per CTA iteration\n", group);
@@ -445,8 +445,9 @@ static int check_cta(const char* name, int n, bool chirp_mode, double tol) {
           std::vector<long> ri, wi2;
           for (int l = 0; l < 32; ++l) {
             const int g = warp * 32 + l, tl = g / per, q = g - tl * per, i = q / stride, j = q - i * stride;
-            ri.push_back(cta::padded(tl * len + (k * m + i) * stride + j));
-            wi2.push_back(cta::padded(tl * len + (i * R + k) * stride + j));
+            const int er = tl * len + (k * m + i) * stride + j, ew = tl * len + (i * R + k) * stride + j;
+            ri.push_back(a.pad ? cta::padded(er) : er);
+            wi2.push_back(a.pad ? cta::padded(ew) : ew);
           }
           worst_r = std::max(worst_r, conflict_degree<(int)sizeof(V)>(ri));
           worst_w = std::max(worst_w, conflict_degree<(int)sizeof(V)>(wi2));
