@@ -111,9 +111,11 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
     return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 8, 1>>::ops(8, 4);
   }
   if (n == ((size_t)1 << 16)) {
-    // 256 x 256 with 16 x 16 register tiles: four 128-thread groups (the f64 shape); 64-byte tile rows as at 2^20
-    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4>>::ops(128, 64);
-    return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true>>::ops(128, 64);   // ring 64: 47 %, ring 128: 51 %
+    // 256 x 256 with 16 x 16 register tiles, four 128-thread groups, 64-byte tile rows as at 2^20.  Measured on B200
+    // (profiles/r02_sizes_cta_and_2pow16.txt): TMA staging 56.5 %, direct loads 51.7 % (ring 128; 47 % at ring 64),
+    // two launches per chunk 33.9 % of the measured HBM peak.
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true>>::ops(128, 64);
+    return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4>>::ops(128, 64);
   }
   return nullptr;
 }
