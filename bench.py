@@ -209,7 +209,10 @@ def run_distributed(args, rank, local_rank, world, barrier, log2n=None, steps=No
     from fourier_b200.distributed import CudaBackend, DistributedFft
     k = log2n or args.log2n
     steps = steps or args.steps
-    n1, n2 = 1 << (k // 2), 1 << (k - k // 2)
+    # N = n1 * n2: rows of length n2 = 2^16 run on the persistent two-pass kernel (0.60 ms per batch of N/P samples on
+    # 8 GPUs, against 0.87 ms for 2^15-point rows on the two-launch tile kernels: profiles/r02_c5_sweep_8gpu.json)
+    k2 = 16 if k >= 26 else k - k // 2
+    n1, n2 = 1 << (k - k2), 1 << k2
     n = n1 * n2
     blk = n // world
     plan = DistributedFft(n1, n2, rank, world, CudaBackend("f32"), exchange=args.exchange, chunks=args.chunks or None)
