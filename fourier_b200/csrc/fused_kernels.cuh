@@ -170,20 +170,22 @@ template <typename T> struct FusedArgs {
 //          cp.async.bulk.prefetch.tensor; pass 2: the L2-resident intermediate, ld.global.cg), one exchange buffer
 //          per group and no lock.  Wins for f64 (four 128-thread groups hide the load latency: +4 %), loses for f32
 //          (two 256-thread groups: -12 %), same profile file.
-template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool DIRECT_ = false>
+// RB_: second radix of the register tile when the tile length L = R_ * RB_ is not a square (L = 128 = 16 x 8,
+//      512 = 32 x 16): N = L^2 = 2^14, 2^18.
+template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool DIRECT_ = false, int RB_ = R_>
 struct FusedCfg {
   using T = T_;
   static constexpr bool DIRECT = DIRECT_;
   static_assert(!DIRECT_ || EXB_ == G_, "direct loads: one exchange buffer per group");
-  static constexpr int R = R_, C = C_, G = G_, EXB = EXB_;
-  static constexpr long L = (long)R * R, N1 = L, N2 = L, N = N1 * N2;
-  template <bool FWD> using Tile = TileFFT<T, R, R, R, C, FWD>;   // same register tile for both passes
+  static constexpr int R = R_, RA = R_, RB = RB_, E = RA > RB ? RA : RB, C = C_, G = G_, EXB = EXB_;
+  static constexpr long L = (long)RA * RB, N1 = L, N2 = L, N = N1 * N2;
+  template <bool FWD> using Tile = TileFFT<T, RA, RB, E, C, FWD>;   // same register tile for both passes
   using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
   // pass 2: scatter block-fast (row stride = 2 mod 16 for 8-byte, odd for 16-byte elements: conflict-free for
   // lanes = 8 positions x 4 FFTs), gather col-fast
   using Lay2 = ExLayout<R * C + (sizeof(T_) == 4 ? 2 : 1), C, 1>;
-  static_assert(C_ == 8 && R_ % 8 == 0, "the blocked intermediate needs 8-column tiles");
-  static constexpr int GT = R * C;                    // threads per group
+  static_assert(C_ == 8 && RB_ % 8 == 0, "the blocked intermediate needs 8-column tiles");
+  static constexpr int GT = Tile<true>::THREADS;      // threads per group
   static constexpr int CONSUMERS = G * GT;
   static constexpr int AUX = ((G + 1 + 3) / 4) * 128;  // G producer warps + 1 signaller warp, in whole warpgroups
   static constexpr int THREADS = CONSUMERS + AUX;
@@ -196,18 +198,21 @@ struct FusedCfg {
   static constexpr int REGS_CONSUMER = REGS_CONSUMER_RAW > 232 ? 232 : REGS_CONSUMER_RAW;
   static constexpr int T1 = (int)(N2 / C), T2 = (int)(N1 / C);
   static constexpr uint32_t TILE_BYTES = (uint32_t)(sizeof(cpx<T>) * C * L);
-  static constexpr uint32_t TAB_BYTES = (uint32_t)(sizeof(cpx<T>) * C * R);   // one tile table (base or step)
+  static constexpr int TAB_BASE = C * RA, TAB_STEP = C * RB, TAB_ELEMS = TAB_BASE + TAB_STEP;   // [base | step] of a tile
+  static constexpr uint32_t TAB_BASE_BYTES = (uint32_t)(sizeof(cpx<T>) * TAB_BASE), TAB_STEP_BYTES = (uint32_t)(sizeof(cpx<T>) * TAB_STEP);
+  static constexpr uint32_t TAB_BYTES = TAB_BASE_BYTES + TAB_STEP_BYTES;
   static constexpr int EX1 = Tile<true>::template smem_elems<Lay1>(), EX2 = Tile<true>::template smem_elems<Lay2>();
   static constexpr int EX_ELEMS = EX1 > EX2 ? EX1 : EX2;
   static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * EX_ELEMS + 127) / 128) * 128;
-  static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * (R / 2) * R;
+  static constexpr int TWA_PAIRS = (RA / 2) * RB;
+  static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * TWA_PAIRS;
   static constexpr size_t BUF_BYTES = DIRECT ? 0 : (size_t)TILE_BYTES;   // per-group staging buffer
   // layout: staging[G] | exchange[EXB] | twa | tile tables [G][2 (double buffer)][base, step] | control
   static constexpr size_t OFF_EX = (size_t)G * BUF_BYTES;
   static constexpr size_t OFF_TWA = OFF_EX + (size_t)EXB * EX_BYTES;
   static constexpr size_t OFF_TAB = OFF_TWA + TWA_BYTES;
-  static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 2 * 2 * TAB_BYTES;
-  static constexpr size_t SMEM_BYTES = OFF_CTL + 1024 /* control block: G * sizeof(GroupCtl) + locks */;
+  static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 2 * TAB_BYTES;
+  static constexpr size_t SMEM_BYTES = OFF_CTL + 2048 /* control block: G * sizeof(GroupCtl) + locks */;
   static constexpr int BOX_ROWS = L < 256 ? (int)L : 256;   // TMA box limit: 256 per dimension
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
@@ -240,21 +245,21 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   if constexpr (Cfg::DIRECT) {
     // nothing to stage, the consumers read global memory themselves; only the tile tables of a pass-1 tile travel
     if (wi.pass == 2) { mbar_arrive(&ctl->full); return; }
-    mbar_arrive_expect_tx(&ctl->full, 2 * Cfg::TAB_BYTES);
-    bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
-    bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TAB_BYTES);
+    bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE, Cfg::TAB_BASE_BYTES, &ctl->full);
+    bulk_load(tab + Cfg::TAB_BASE, a.tstep + (size_t)wi.tile * Cfg::TAB_STEP, Cfg::TAB_STEP_BYTES, &ctl->full);
     return;
   }
   // (the group's reads of `dst` are ordered before this refill by the empty-mbarrier wait of the caller)
   if (wi.pass == 1) {
-    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + 2 * Cfg::TAB_BYTES);
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + Cfg::TAB_BYTES);
     constexpr int BOX = Cfg::BOX_ROWS;
     const int x = wi.tile * C * 2;  // in scalars of T
 #pragma unroll
     for (int r0 = 0; r0 < (int)Cfg::L; r0 += BOX)
       tma_load_2d_first(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), &ctl->full);
-    bulk_load(tab, a.tbase + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
-    bulk_load(tab + C * Cfg::R, a.tstep + (size_t)wi.tile * C * Cfg::R, Cfg::TAB_BYTES, &ctl->full);
+    bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE, Cfg::TAB_BASE_BYTES, &ctl->full);
+    bulk_load(tab + Cfg::TAB_BASE, a.tstep + (size_t)wi.tile * Cfg::TAB_STEP, Cfg::TAB_STEP_BYTES, &ctl->full);
   } else {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES);
     const V* src = a.scratch + (size_t)d.slot * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
@@ -303,9 +308,9 @@ template <class Cfg, bool FWD> struct FusedMath {
   static FB_HD void stage_a(Tile& f, int pass, int t, const TwPair<T>* twa) {
     if (pass == 1) f.template stage_a<kMapCF, true>(t, twa); else f.template stage_a<kMap2, true>(t, twa);
   }
-  // plane layout of the pair table `src` ((R / 2) * R pairs), entry i
+  // plane layout of the pair table `src` (TWA_PAIRS pairs), entry i
   static FB_HD void relayout_twa(void* planes, const TwPair<T>* src, int i) {
-    TwPlanes<T>::put(planes, (R / 2) * R, i, src[i]);
+    TwPlanes<T>::put(planes, Cfg::TWA_PAIRS, i, src[i]);
   }
   static FB_HD void scatter(const Tile& f, int pass, int t, V* exch) {
     if (pass == 1) f.template scatter<kMapCF, typename Cfg::Lay1>(t, exch);
@@ -318,7 +323,7 @@ template <class Cfg, bool FWD> struct FusedMath {
   // pass 1: inter-pass twiddle (factored, tables tb = [base | step]) and store into the ring slot `slot_base`
   // (blocked layout, kept in L2)
   static FB_HD void store1(const Tile& f, int t, V* slot_base, int tile, const V* tb) {
-    f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * 64, tb, tb + C * R);
+    f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * 64, tb, tb + Cfg::TAB_BASE);
   }
   // pass 2: transposed store of the result, X[k1 + N1 * k2], streaming
   static FB_HD void store2(const Tile& f, int t, V* out_b, int tile, bool do_scale, T scale) {
@@ -359,7 +364,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   unsigned char* staging = base;                                             // [G][BUF_BYTES]
   unsigned char* exch_pool = base + Cfg::OFF_EX;
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
-  V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][2][2][C*R]
+  V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][2][base | step]
   GroupCtl* ctl_all = reinterpret_cast<GroupCtl*>(base + Cfg::OFF_CTL);
   int* locks = reinterpret_cast<int*>(ctl_all + G);   // one per exchange buffer
 
@@ -377,7 +382,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     for (int i = 0; i < Cfg::EXB; ++i) locks[i] = 0;
     fence_barrier_init();
   }
-  for (int i = tid; i < (R / 2) * R; i += Cfg::THREADS) Math::relayout_twa(twa, a.twa, i);   // stage-A twiddles live in smem
+  for (int i = tid; i < Cfg::TWA_PAIRS; i += Cfg::THREADS) Math::relayout_twa(twa, a.twa, i);   // stage-A twiddles live in smem
   __syncthreads();
 
   unsigned* queue = a.counters;
@@ -396,7 +401,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       const int g = pw;
       GroupCtl* ctl = &ctl_all[g];
       V* stage_g = reinterpret_cast<V*>(staging + (size_t)g * Cfg::BUF_BYTES);
-      V* tab_g = tabs + (size_t)g * 2 * 2 * C * R;
+      V* tab_g = tabs + (size_t)g * 2 * Cfg::TAB_ELEMS;
       uint32_t n_p1 = 0;
       unsigned w_next = atomicAdd(queue, 1u);
       for (uint32_t it = 0;; ++it) {
@@ -419,7 +424,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
           }
         }
         FB_PTRACE(2);
-        issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * 2 * C * R, ctl);
+        issue_tile<Cfg>(wi, &in_map, a, stage_g, tab_g + (size_t)(n_p1 & 1) * Cfg::TAB_ELEMS, ctl);
         FB_PTRACE(3);
         n_p1 += wi.pass == 1;
         if (wi.pass < 0) break;
@@ -463,7 +468,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   const int g = tid / GT;
   const int t = tid - g * GT;
   V* stage_g = reinterpret_cast<V*>(staging + (size_t)g * Cfg::BUF_BYTES);
-  V* tab_g = tabs + (size_t)g * 2 * 2 * C * R;
+  V* tab_g = tabs + (size_t)g * 2 * Cfg::TAB_ELEMS;
   GroupCtl* ctl = &ctl_all[g];
   const int bar_id = 1 + g;
   V* exch = reinterpret_cast<V*>(exch_pool + (size_t)(g % Cfg::EXB) * Cfg::EX_BYTES);
@@ -540,7 +545,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     // ---- stage B and the stores ---------------------------------------------------------------------------------
     f.stage_b();
     if (wi.pass == 1) {
-      const V* tb = tab_g + (size_t)(k_p1 & 1) * 2 * C * R;
+      const V* tb = tab_g + (size_t)(k_p1 & 1) * Cfg::TAB_ELEMS;
       ++k_p1;
       Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb);
       // report "stores issued"; the last warp of the group hands the tile to the signaller warp

@@ -26,21 +26,24 @@ inline std::vector<TwPair<T>> make_twa(int ra, int rb) {
 }
 
 // Factored inter-pass twiddles of the persistent kernel, contiguous per pass-1 tile of `cc` columns
-// (n2 = tile*cc + col, stage radix rr):  tbase[tile][col][p] = w_N^{n2*p},  tstep[tile][r][col] = w_N^{rr*n2*r};
-// base_pcol: tbase[tile][p][col] instead.
+// (n2 = tile*cc + col, register tile ra x rb):  tbase[tile][p][col] = w_N^{n2*p} (p < ra; [col][p] if !base_pcol),
+// tstep[tile][r][col] = w_N^{ra*n2*r} (r < rb).
 template <typename T>
-inline void make_factored_twiddles(size_t n, size_t n2, int rr, int cc, std::vector<cpx<T>>& tbase,
+inline void make_factored_twiddles(size_t n, size_t n2, int ra, int rb, int cc, std::vector<cpx<T>>& tbase,
                                    std::vector<cpx<T>>& tstep, bool base_pcol = false) {
-  tbase.assign(n2 * rr, cpx<T>());
-  tstep.assign(n2 * rr, cpx<T>());
+  tbase.assign(n2 * ra, cpx<T>());
+  tstep.assign(n2 * rb, cpx<T>());
   for (size_t c2 = 0; c2 < n2; ++c2) {
     const size_t tile = c2 / cc, col = c2 % cc;
-    for (int q = 0; q < rr; ++q) {
+    for (int q = 0; q < ra; ++q) {
       double re, im;
       host_twiddle(c2 * (size_t)q, n, &re, &im);
-      tbase[base_pcol ? (tile * rr + q) * cc + col : (tile * cc + col) * rr + q] = mk<T>((T)re, (T)im);
-      host_twiddle((size_t)rr * c2 * (size_t)q, n, &re, &im);
-      tstep[(tile * rr + q) * cc + col] = mk<T>((T)re, (T)im);
+      tbase[base_pcol ? (tile * ra + q) * cc + col : (tile * cc + col) * ra + q] = mk<T>((T)re, (T)im);
+    }
+    for (int q = 0; q < rb; ++q) {
+      double re, im;
+      host_twiddle((size_t)ra * c2 * (size_t)q, n, &re, &im);
+      tstep[(tile * rb + q) * cc + col] = mk<T>((T)re, (T)im);
     }
   }
 }

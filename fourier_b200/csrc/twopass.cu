@@ -96,7 +96,7 @@ template <class Cfg> struct FusedImpl {
     return cudaGetLastError();
   }
   static const FusedOps<T>* ops(int ring, int lag) {
-    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::R, Cfg::R, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
+    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::RA, Cfg::RB, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
                                   true, &prepare, &launch};
     return &o;
   }
@@ -117,6 +117,16 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
     if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true>>::ops(128, 64);
     return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4>>::ops(128, 64);
   }
+  if (n == ((size_t)1 << 18)) {
+    // 512 x 512 with 32 x 16 register tiles: three 128-thread groups with TMA staging, or four with direct loads
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 32, 8, 4, 8, 4, true, 16>>::ops(32, 16);
+    return FusedImpl<fused::FusedCfg<float, 32, 8, 3, 8, 3, false, 16>>::ops(32, 16);
+  }
+  if (n == ((size_t)1 << 14)) {
+    // 128 x 128 with 16 x 8 register tiles: eight 64-thread groups
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 8, 8, 8, true, 8>>::ops(512, 256);
+    return FusedImpl<fused::FusedCfg<float, 16, 8, 8, 8, 8, false, 8>>::ops(512, 256);
+  }
   return nullptr;
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
@@ -124,6 +134,11 @@ template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
     // default: four 128-thread groups loading directly from global memory, one exchange buffer each
     if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
     return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>::ops(64, 32);
+  }
+  if (n == ((size_t)1 << 14)) {
+    // 128 x 128 with 16 x 8 register tiles: eight 64-thread groups loading directly, or five with TMA staging
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<double, 16, 8, 5, 4, 5, false, 8>>::ops(256, 128);
+    return FusedImpl<fused::FusedCfg<double, 16, 8, 8, 4, 8, true, 8>>::ops(256, 128);
   }
   return nullptr;
 }
@@ -157,11 +172,13 @@ cudaError_t Plan<T>::init_twopass() {
   fused_ops_ = nullptr;
   if (env_int("FOURIER_B200_FUSED", 1) != 0) {
     const FusedOps<T>* f = fused_lookup<T>(n_);
-    if (f && f->n1 == n1_ && f->n2 == n2_ && f->prepare() == cudaSuccess) {
+    if (f && f->prepare() == cudaSuccess) {
+      // the persistent kernel has its own split and register tile (the tile kernels above stay as its fallback)
+      FB_CHECK((upload_vec<T, TwPair<T>>(tw_f_, make_twa<T>(f->ra, f->rb))));
       // factored inter-pass twiddles, contiguous per pass-1 tile of `tile_c` columns:
       //   tbase[tile][col][p] = w_N^{n2*p},  tstep[tile][r][col] = w_N^{R*n2*r},  n2 = tile*tile_c + col
       std::vector<cpx<T>> tb, ts;
-      make_factored_twiddles<T>(n_, n2_, f->ra, f->tile_c, tb, ts, f->base_pcol);
+      make_factored_twiddles<T>(n_, f->n2, f->ra, f->rb, f->tile_c, tb, ts, f->base_pcol);
       FB_CHECK((upload_vec<T, cpx<T>>(tbase_, tb)));
       FB_CHECK((upload_vec<T, cpx<T>>(tstep_, ts)));
       fused_ops_ = f;
@@ -196,7 +213,7 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
     FB_CHECK(cudaMemsetAsync(counters_.data(), 0, cbytes, s));
     fused::FusedArgs<T> a;
     a.in = in; a.out = out; a.scratch = (C*)work_.data();
-    a.twa = (const TwPair<T>*)tw_a_.data();
+    a.twa = (const TwPair<T>*)tw_f_.data();
     a.tbase = (const C*)tbase_.data(); a.tstep = (const C*)tstep_.data();
     a.counters = (unsigned*)counters_.data();
     a.trace = nullptr;
@@ -207,7 +224,7 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
       a.trace = (long long*)trace_.data();
     }
     a.batch = (int)batch; a.ring = ring; a.lag = lag; a.scale = scale; a.do_scale = do_scale ? 1 : 0;
-    const size_t tiles = batch * (n1_ + n2_) / (size_t)f->tile_c;
+    const size_t tiles = batch * (f->n1 + f->n2) / (size_t)f->tile_c;
     const int grid = (int)std::min<size_t>((size_t)sm_count_, std::max<size_t>(1, tiles / 2));
     FB_CHECK(f->launch(a, fwd, grid, s));
     launches_ += 1;

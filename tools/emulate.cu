@@ -314,14 +314,14 @@ static int check_fused(const char* name, double tol) {
     printf("  per warp: %.1f lines of 128 B per pass-1 store instruction (%d B stored), %.1f different pass-2 stage twiddles\n",
            (double)lines / (GT / 32), 32 * (int)sizeof(V), (double)twiddles / (GT / 32));
   }
-  auto twa_pairs = make_twa<T>(R, R);
+  auto twa_pairs = make_twa<T>(Cfg::RA, Cfg::RB);
   std::vector<TwPair<T>> twa(twa_pairs.size());     // the kernel re-lays the table out in 8-byte planes
   for (int i = 0; i < (int)twa_pairs.size(); ++i) fused::FusedMath<Cfg, true>::relayout_twa(twa.data(), twa_pairs.data(), i);
   std::vector<V> tbase, tstep;
-  make_factored_twiddles<T>((size_t)N, (size_t)N2, R, C, tbase, tstep, true);
+  make_factored_twiddles<T>((size_t)N, (size_t)N2, Cfg::RA, Cfg::RB, C, tbase, tstep, true);
   int bad = 0;
   for (int fwd = 1; fwd >= 0; --fwd) {
-    std::vector<V> x(N), scratch(N), out(N), staging((size_t)C * Cfg::L), tab(2 * (size_t)C * R);
+    std::vector<V> x(N), scratch(N), out(N), staging((size_t)C * Cfg::L), tab((size_t)Cfg::TAB_ELEMS);
     std::vector<V> exch(Cfg::EX_ELEMS);
     fill<T>(x, 41 + fwd);
     const T scale = (T)0.5;
@@ -344,7 +344,8 @@ static int check_fused(const char* name, double tol) {
     for (int tile = 0; tile < Cfg::T1; ++tile) {        // pass 1: TMA box = rows n1, columns tile*C .. +C
       for (long r = 0; r < N1; ++r)
         for (int c = 0; c < C; ++c) staging[r * C + c] = x[r * N2 + (long)tile * C + c];
-      for (int i = 0; i < C * R; ++i) { tab[i] = tbase[(size_t)tile * C * R + i]; tab[C * R + i] = tstep[(size_t)tile * C * R + i]; }
+      for (int i = 0; i < Cfg::TAB_BASE; ++i) tab[i] = tbase[(size_t)tile * Cfg::TAB_BASE + i];
+      for (int i = 0; i < Cfg::TAB_STEP; ++i) tab[Cfg::TAB_BASE + i] = tstep[(size_t)tile * Cfg::TAB_STEP + i];
       if (fwd) run_tile(std::true_type{}, 1, tile); else run_tile(std::false_type{}, 1, tile);
     }
     for (int tile = 0; tile < Cfg::T2; ++tile) {        // pass 2: bulk copy of C*N2 contiguous samples
@@ -550,6 +551,9 @@ int main() {
   bad += check_fused<fused::FusedCfg<double, 16, 8, 3, 4, 3>>("fused f64 2^16", 5e-15);
   bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 8, 2, true>>("fused f32 2^20", 2e-6);
   bad += check_fused<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>("fused f64 2^16", 5e-15);
+  bad += check_fused<fused::FusedCfg<float, 32, 8, 3, 8, 3, false, 16>>("fused f32 2^18", 2e-6);
+  bad += check_fused<fused::FusedCfg<float, 16, 8, 8, 8, 8, false, 8>>("fused f32 2^14", 2e-6);
+  bad += check_fused<fused::FusedCfg<double, 16, 8, 8, 4, 8, true, 8>>("fused f64 2^14", 5e-15);
   bad += check_fused<fused::FusedCfg<float, 16, 8, 4, FB_PAD16, 4, true>>("fused f32 2^16", 2e-6);
   bad += check_fused<fused::FusedCfg<float, 16, 8, 4, FB_PAD16, 4>>("fused f32 2^16", 2e-6);
   bad += check_queue();
