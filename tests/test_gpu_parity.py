@@ -286,6 +286,38 @@ def test_alternative_persistent_kernel_configuration(monkeypatch, real, n):
         assert rel_err(got[7], O.transform(x[7], int(code))) < TOL[real]
 
 
+def test_misaligned_device_pointer_is_refused():
+    """the kernels use 16-byte vector accesses / TMA on device buffers; a slice that starts at an odd f32
+    sample is only 8-byte aligned and must be refused up front (no launch, no sticky CUDA error)."""
+    import torch
+    p = create("f32", 1 << 20)
+    big = torch.zeros(2 * (1 << 20) + 2, dtype=torch.complex64, device="cuda")
+    x, y = big[1:1 + (1 << 20)], torch.empty(1 << 20, dtype=torch.complex64, device="cuda")
+    assert x.data_ptr() % 16 == 8
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        p.transform(x, y, T.Fft)
+    with pytest.raises(RuntimeError, match="16-byte aligned"):
+        p.transform(y, x, T.Fft)
+    torch.cuda.synchronize()                      # the context is still healthy
+    ok = torch.empty(1 << 20, dtype=torch.complex64, device="cuda")
+    fb.fill_input(ok.view(1, -1))
+    p.transform(ok, y, T.Fft)
+    torch.cuda.synchronize()
+    want = O.transform(O.fill_input(1, 1 << 20, np.complex64)[0], O.FFT)
+    assert rel_err(y.cpu().numpy(), want) < TOL["f32"]
+
+
+def test_kernel_names_follow_the_path():
+    names = {(r, n): create(r, n).kernel_name() for r, n in
+             [("f32", 1 << 20), ("f64", 1 << 16), ("f32", 1 << 16), ("f32", 1024), ("f32", 1009), ("f32", 729),
+              ("f64", 1009), ("f32", 1 << 15), ("f32", 3 ** 9)]}
+    assert "fused_twopass_kernel" in names[("f32", 1 << 20)] and "fused_twopass_kernel" in names[("f64", 1 << 16)]
+    assert "fused_twopass_kernel" in names[("f32", 1 << 16)]
+    assert "onchip_fft_kernel" in names[("f32", 1024)] and "bluestein_fused_kernel" in names[("f32", 1009)]
+    assert "cta_fft_kernel" in names[("f32", 729)] and "chirp" in names[("f64", 1009)]
+    assert "tile_kernel" in names[("f32", 1 << 15)] and "stockham_stage_kernel" in names[("f32", 3 ** 9)]
+
+
 def test_error_conventions():
     L = _lib.load()
     assert not L.fourier_create_float(0)          # reference hangs on 0 (autosort/mod.rs:112): refused
