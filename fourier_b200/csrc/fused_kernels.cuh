@@ -147,7 +147,8 @@ template <typename T> struct FusedArgs {
   const cpx<T>* in;
   cpx<T>* out;
   cpx<T>* scratch;            // RING transforms
-  const TwPair<T>* twa;       // stage-A twiddles of a length-L tile (both passes: N1 == N2 == L)
+  const TwPair<T>* twa;       // stage-A twiddles of the pass-1 register tile (length N1)
+  const TwPair<T>* twa2;      // ... of the pass-2 register tile (length N2; same table when the tiles are equal)
   const cpx<T>* tbase;        // [tile][col][p]  w_N^{n2*p}        (pass-1 tile tables, contiguous per tile)
   const cpx<T>* tstep;        // [tile][r][col]  w_N^{R*n2*r}
   unsigned* counters;         // [0] queue head, [1 .. 1+B) done1, [1+B .. 1+2B) done2
@@ -172,20 +173,26 @@ template <typename T> struct FusedArgs {
 //          (two 256-thread groups: -12 %), same profile file.
 // RB_: second radix of the register tile when the tile length L = R_ * RB_ is not a square (L = 128 = 16 x 8,
 //      512 = 32 x 16): N = L^2 = 2^14, 2^18.
-template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool DIRECT_ = false, int RB_ = R_>
+// RA2_, RB2_, E1_, E2_: a different register tile for pass 2 (N2 = RA2_ * RB2_ != N1 = R_ * RB_: the odd powers of
+//      two, e.g. 2^15 = 128 x 256); E1_ / E2_ samples per thread chosen so that both tiles have the same number of
+//      threads per FFT (TP = N1 / E1 = N2 / E2), i.e. the same group size.
+template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool DIRECT_ = false, int RB_ = R_,
+          int RA2_ = R_, int RB2_ = RB_, int E1_ = (R_ > RB_ ? R_ : RB_), int E2_ = (RA2_ > RB2_ ? RA2_ : RB2_)>
 struct FusedCfg {
   using T = T_;
   static constexpr bool DIRECT = DIRECT_;
   static_assert(!DIRECT_ || EXB_ == G_, "direct loads: one exchange buffer per group");
-  static constexpr int R = R_, RA = R_, RB = RB_, E = RA > RB ? RA : RB, C = C_, G = G_, EXB = EXB_;
-  static constexpr long L = (long)RA * RB, N1 = L, N2 = L, N = N1 * N2;
-  template <bool FWD> using Tile = TileFFT<T, RA, RB, E, C, FWD>;   // same register tile for both passes
-  using Lay1 = ExLayout<R * C + PAD1_, C, 1>;                      // pass 1: scatter and gather col-fast
+  static constexpr int RA = R_, RB = RB_, RA2 = RA2_, RB2 = RB2_, C = C_, G = G_, EXB = EXB_;
+  static constexpr long N1 = (long)RA * RB, N2 = (long)RA2 * RB2, N = N1 * N2;
+  template <bool FWD> using Tile1 = TileFFT<T, RA, RB, E1_, C, FWD>;     // pass 1: C columns, FFT length N1
+  template <bool FWD> using Tile2 = TileFFT<T, RA2, RB2, E2_, C, FWD>;   // pass 2: C rows, FFT length N2
+  static_assert(Tile1<true>::THREADS == Tile2<true>::THREADS, "both register tiles must use the same group size");
+  using Lay1 = ExLayout<RA * C + PAD1_, C, 1>;                     // pass 1: scatter and gather col-fast
   // pass 2: scatter block-fast (row stride = 2 mod 16 for 8-byte, odd for 16-byte elements: conflict-free for
   // lanes = 8 positions x 4 FFTs), gather col-fast
-  using Lay2 = ExLayout<R * C + (sizeof(T_) == 4 ? 2 : 1), C, 1>;
-  static_assert(C_ == 8 && RB_ % 8 == 0, "the blocked intermediate needs 8-column tiles");
-  static constexpr int GT = Tile<true>::THREADS;      // threads per group
+  using Lay2 = ExLayout<RA2 * C + (sizeof(T_) == 4 ? 2 : 1), C, 1>;
+  static_assert(C_ == 8 && RB_ % 8 == 0 && RB2_ % 8 == 0, "the blocked intermediate needs 8-column tiles");
+  static constexpr int GT = Tile1<true>::THREADS;     // threads per group
   static constexpr int CONSUMERS = G * GT;
   static constexpr int AUX = ((G + 1 + 3) / 4) * 128;  // G producer warps + 1 signaller warp, in whole warpgroups
   static constexpr int THREADS = CONSUMERS + AUX;
@@ -197,23 +204,25 @@ struct FusedCfg {
   static constexpr int REGS_CONSUMER_RAW = ((LAUNCH_REGS * THREADS - REGS_PRODUCER * AUX) / CONSUMERS / 8) * 8;
   static constexpr int REGS_CONSUMER = REGS_CONSUMER_RAW > 232 ? 232 : REGS_CONSUMER_RAW;
   static constexpr int T1 = (int)(N2 / C), T2 = (int)(N1 / C);
-  static constexpr uint32_t TILE_BYTES = (uint32_t)(sizeof(cpx<T>) * C * L);
+  static constexpr uint32_t TILE1_BYTES = (uint32_t)(sizeof(cpx<T>) * C * N1), TILE2_BYTES = (uint32_t)(sizeof(cpx<T>) * C * N2);
   static constexpr int TAB_BASE = C * RA, TAB_STEP = C * RB, TAB_ELEMS = TAB_BASE + TAB_STEP;   // [base | step] of a tile
   static constexpr uint32_t TAB_BASE_BYTES = (uint32_t)(sizeof(cpx<T>) * TAB_BASE), TAB_STEP_BYTES = (uint32_t)(sizeof(cpx<T>) * TAB_STEP);
   static constexpr uint32_t TAB_BYTES = TAB_BASE_BYTES + TAB_STEP_BYTES;
-  static constexpr int EX1 = Tile<true>::template smem_elems<Lay1>(), EX2 = Tile<true>::template smem_elems<Lay2>();
+  static constexpr int EX1 = Tile1<true>::template smem_elems<Lay1>(), EX2 = Tile2<true>::template smem_elems<Lay2>();
   static constexpr int EX_ELEMS = EX1 > EX2 ? EX1 : EX2;
   static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * EX_ELEMS + 127) / 128) * 128;
-  static constexpr int TWA_PAIRS = (RA / 2) * RB;
-  static constexpr size_t TWA_BYTES = sizeof(TwPair<T>) * TWA_PAIRS;
-  static constexpr size_t BUF_BYTES = DIRECT ? 0 : (size_t)TILE_BYTES;   // per-group staging buffer
-  // layout: staging[G] | exchange[EXB] | twa | tile tables [G][2 (double buffer)][base, step] | control
+  static constexpr int TWA1_PAIRS = (RA / 2) * RB, TWA2_PAIRS = (RA2 / 2) * RB2;
+  static constexpr bool SAME_TILE = RA == RA2 && RB == RB2 && E1_ == E2_;   // one stage-twiddle table serves both passes
+  static constexpr size_t TWA1_BYTES = sizeof(TwPair<T>) * TWA1_PAIRS,
+                          TWA_BYTES = TWA1_BYTES + (SAME_TILE ? 0 : sizeof(TwPair<T>) * TWA2_PAIRS);
+  static constexpr size_t BUF_BYTES = DIRECT ? 0 : (size_t)(TILE1_BYTES > TILE2_BYTES ? TILE1_BYTES : TILE2_BYTES);   // staging
+  // layout: staging[G] | exchange[EXB] | twa (tile 1, tile 2) | tile tables [G][2 (double buffer)][base, step] | control
   static constexpr size_t OFF_EX = (size_t)G * BUF_BYTES;
   static constexpr size_t OFF_TWA = OFF_EX + (size_t)EXB * EX_BYTES;
   static constexpr size_t OFF_TAB = OFF_TWA + TWA_BYTES;
   static constexpr size_t OFF_CTL = OFF_TAB + (size_t)G * 2 * TAB_BYTES;
   static constexpr size_t SMEM_BYTES = OFF_CTL + 2048 /* control block: G * sizeof(GroupCtl) + locks */;
-  static constexpr int BOX_ROWS = L < 256 ? (int)L : 256;   // TMA box limit: 256 per dimension
+  static constexpr int BOX_ROWS = N1 < 256 ? (int)N1 : 256;   // TMA box limit: 256 per dimension
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
@@ -252,22 +261,22 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   }
   // (the group's reads of `dst` are ordered before this refill by the empty-mbarrier wait of the caller)
   if (wi.pass == 1) {
-    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES + Cfg::TAB_BYTES);
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE1_BYTES + Cfg::TAB_BYTES);
     constexpr int BOX = Cfg::BOX_ROWS;
     const int x = wi.tile * C * 2;  // in scalars of T
 #pragma unroll
-    for (int r0 = 0; r0 < (int)Cfg::L; r0 += BOX)
+    for (int r0 = 0; r0 < (int)Cfg::N1; r0 += BOX)
       tma_load_2d_first(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), &ctl->full);
     bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE, Cfg::TAB_BASE_BYTES, &ctl->full);
     bulk_load(tab + Cfg::TAB_BASE, a.tstep + (size_t)wi.tile * Cfg::TAB_STEP, Cfg::TAB_STEP_BYTES, &ctl->full);
   } else {
-    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE_BYTES);
+    mbar_arrive_expect_tx(&ctl->full, Cfg::TILE2_BYTES);
     const V* src = a.scratch + (size_t)d.slot * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
     constexpr uint32_t PIECE = 16384;
 #pragma unroll
-    for (uint32_t o = 0; o < Cfg::TILE_BYTES; o += PIECE)
+    for (uint32_t o = 0; o < Cfg::TILE2_BYTES; o += PIECE)
       bulk_load((unsigned char*)dst + o, (const unsigned char*)src + o,
-                Cfg::TILE_BYTES - o < PIECE ? Cfg::TILE_BYTES - o : PIECE, &ctl->full);
+                Cfg::TILE2_BYTES - o < PIECE ? Cfg::TILE2_BYTES - o : PIECE, &ctl->full);
   }
 }
 
@@ -281,52 +290,55 @@ __device__ __forceinline__ const unsigned* dep_counter(const WorkItem& wi, const
   return nullptr;
 }
 
-// The arithmetic of one consumer thread between the barriers of the kernel.  __host__ __device__: the kernel
-// below and tools/emulate.cu (CPU, thread by thread) run exactly this code.
+// The arithmetic of one consumer thread between the barriers of the kernel, per pass (Pass<1>: column tiles on
+// Tile1, Pass<2>: row tiles on Tile2).  __host__ __device__: the kernel below and tools/emulate.cu (CPU, thread by
+// thread) run exactly this code.
 template <class Cfg, bool FWD> struct FusedMath {
   using T = typename Cfg::T;
   using V = cpx<T>;
-  using Tile = typename Cfg::template Tile<FWD>;
-  static constexpr int C = Cfg::C, R = Cfg::R;
+  using Tile1 = typename Cfg::template Tile1<FWD>;
+  using Tile2 = typename Cfg::template Tile2<FWD>;
+  static constexpr int C = Cfg::C;
   static constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
-  static constexpr int kMap2 = kMapBF;     // pass-2 mapping up to the exchange
-  static_assert(Tile::kBlockFastOk, "tile shape does not fit the block-fast mapping");
+  static_assert(Tile2::kBlockFastOk, "pass-2 tile shape does not fit the block-fast mapping");
 
-  // staging -> registers.  Pass 1: staging = [n1][C] (TMA box); pass 2: the tile's 8 x 8 blocks.
-  // DIRECT: `stage` is the tile's first sample in global memory: C columns of x (row stride N2, read once), or the
-  // tile's 8 x 8 blocks of the intermediate (rewritten by other SMs during the kernel: L2 only).
-  static FB_HD void load(Tile& f, int pass, int t, const V* stage) {
-    if (pass == 1) {
+  template <int PASS, int DUMMY = 0> struct Pass;
+
+  // ---- pass 1: staging = [n1][C] (TMA box), or with DIRECT C columns of x in global memory (row stride N2, read
+  // once); everything col-fast; store = inter-pass twiddle (factored, tables tb = [base | step]) into the blocked
+  // ring slot (kept in L2)
+  template <int DUMMY> struct Pass<1, DUMMY> {
+    using Tile = Tile1;
+    static FB_HD void load(Tile& f, int t, const V* stage) {
       if constexpr (Cfg::DIRECT) f.template load<kMapCF, N2, 1, 1>(t, stage);
       else f.template load<kMapCF, C, 1>(t, stage);
-    } else {
+    }
+    static FB_HD void stage_a(Tile& f, int t, const TwPair<T>* twa) { f.template stage_a<kMapCF, true>(t, twa); }
+    static FB_HD void scatter(const Tile& f, int t, V* exch) { f.template scatter<kMapCF, typename Cfg::Lay1>(t, exch); }
+    static FB_HD void gather(Tile& f, int t, const V* exch) { f.template gather<kMapCF, typename Cfg::Lay1>(t, exch); }
+  };
+  // ---- pass 2: staging (or, DIRECT, the L2-resident ring: rewritten by other SMs during the kernel, L2 only) = the
+  // tile's 8 x 8 blocks; block-fast up to the exchange, col-fast after it; transposed streaming store X[k1 + N1 * k2]
+  template <int DUMMY> struct Pass<2, DUMMY> {
+    using Tile = Tile2;
+    static FB_HD void load(Tile& f, int t, const V* stage) {
       if constexpr (Cfg::DIRECT) f.template load_blocked<kMapBF, 2>(t, stage);
       else f.template load_blocked<kMapBF>(t, stage);
     }
+    static FB_HD void stage_a(Tile& f, int t, const TwPair<T>* twa) { f.template stage_a<kMapBF, true>(t, twa); }
+    static FB_HD void scatter(const Tile& f, int t, V* exch) { f.template scatter<kMapBF, typename Cfg::Lay2>(t, exch); }
+    static FB_HD void gather(Tile& f, int t, const V* exch) { f.template gather<kMapCF, typename Cfg::Lay2>(t, exch); }
+  };
+  static constexpr int kMap2 = kMapBF;
+  // `twa`: stage twiddles in the 8-byte-plane layout (TwPlanes): in both mappings 4 or 8 lanes share a pair.
+  // Plane layout of the pair tables of the two tiles, entry i of tile `which`:
+  static FB_HD void relayout_twa(void* planes, const TwPair<T>* src, int i, int pairs) {
+    TwPlanes<T>::put(planes, pairs, i, src[i]);
   }
-  // `twa`: the stage twiddles in the 8-byte-plane layout (TwPlanes): in both mappings 4 or 8 lanes share a pair
-  static FB_HD void stage_a(Tile& f, int pass, int t, const TwPair<T>* twa) {
-    if (pass == 1) f.template stage_a<kMapCF, true>(t, twa); else f.template stage_a<kMap2, true>(t, twa);
-  }
-  // plane layout of the pair table `src` (TWA_PAIRS pairs), entry i
-  static FB_HD void relayout_twa(void* planes, const TwPair<T>* src, int i) {
-    TwPlanes<T>::put(planes, Cfg::TWA_PAIRS, i, src[i]);
-  }
-  static FB_HD void scatter(const Tile& f, int pass, int t, V* exch) {
-    if (pass == 1) f.template scatter<kMapCF, typename Cfg::Lay1>(t, exch);
-    else f.template scatter<kMap2, typename Cfg::Lay2>(t, exch);
-  }
-  static FB_HD void gather(Tile& f, int pass, int t, const V* exch) {
-    if (pass == 1) f.template gather<kMapCF, typename Cfg::Lay1>(t, exch);
-    else f.template gather<kMapCF, typename Cfg::Lay2>(t, exch);
-  }
-  // pass 1: inter-pass twiddle (factored, tables tb = [base | step]) and store into the ring slot `slot_base`
-  // (blocked layout, kept in L2)
-  static FB_HD void store1(const Tile& f, int t, V* slot_base, int tile, const V* tb) {
+  static FB_HD void store1(const Tile1& f, int t, V* slot_base, int tile, const V* tb) {
     f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * 64, tb, tb + Cfg::TAB_BASE);
   }
-  // pass 2: transposed store of the result, X[k1 + N1 * k2], streaming
-  static FB_HD void store2(const Tile& f, int t, V* out_b, int tile, bool do_scale, T scale) {
+  static FB_HD void store2(const Tile2& f, int t, V* out_b, int tile, bool do_scale, T scale) {
     V* dst = out_b + (size_t)tile * C;
     if (do_scale) f.template store<kMapCF, N1, 1, false, true, 1>(t, dst, nullptr, scale);
     else f.template store<kMapCF, N1, 1, false, false, 1>(t, dst, nullptr, scale);
@@ -351,10 +363,9 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs<typename Cfg::T> a) {
   using T = typename Cfg::T;
   using V = cpx<T>;
-  constexpr int G = Cfg::G, GT = Cfg::GT, C = Cfg::C, R = Cfg::R;
+  constexpr int G = Cfg::G, GT = Cfg::GT, C = Cfg::C;
   constexpr long N = Cfg::N, N2 = Cfg::N2;
   constexpr int T1 = Cfg::T1, T2 = Cfg::T2;
-  using Tile = typename Cfg::template Tile<FWD>;
   using Math = FusedMath<Cfg, FWD>;
 
   // No integer round-trip on this pointer: the compiler must keep the shared address space, otherwise
@@ -363,7 +374,8 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
   unsigned char* base = smem_raw;
   unsigned char* staging = base;                                             // [G][BUF_BYTES]
   unsigned char* exch_pool = base + Cfg::OFF_EX;
-  TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
+  TwPair<T>* twa1 = reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA);
+  TwPair<T>* twa2 = Cfg::SAME_TILE ? twa1 : reinterpret_cast<TwPair<T>*>(base + Cfg::OFF_TWA + Cfg::TWA1_BYTES);
   V* tabs = reinterpret_cast<V*>(base + Cfg::OFF_TAB);                       // [G][2][base | step]
   GroupCtl* ctl_all = reinterpret_cast<GroupCtl*>(base + Cfg::OFF_CTL);
   int* locks = reinterpret_cast<int*>(ctl_all + G);   // one per exchange buffer
@@ -382,7 +394,10 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     for (int i = 0; i < Cfg::EXB; ++i) locks[i] = 0;
     fence_barrier_init();
   }
-  for (int i = tid; i < Cfg::TWA_PAIRS; i += Cfg::THREADS) Math::relayout_twa(twa, a.twa, i);   // stage-A twiddles live in smem
+  // stage-A twiddles of both register tiles live in shared memory (8-byte planes)
+  for (int i = tid; i < Cfg::TWA1_PAIRS; i += Cfg::THREADS) Math::relayout_twa(twa1, a.twa, i, Cfg::TWA1_PAIRS);
+  if constexpr (!Cfg::SAME_TILE)
+    for (int i = tid; i < Cfg::TWA2_PAIRS; i += Cfg::THREADS) Math::relayout_twa(twa2, a.twa2, i, Cfg::TWA2_PAIRS);
   __syncthreads();
 
   unsigned* queue = a.counters;
@@ -419,7 +434,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
           // do not crowd the intermediate out of L2.
           if (wi.pass == 1) {
 #pragma unroll
-            for (int r0 = 0; r0 < (int)Cfg::L; r0 += Cfg::BOX_ROWS)
+            for (int r0 = 0; r0 < (int)Cfg::N1; r0 += Cfg::BOX_ROWS)
               tma_prefetch_2d(&in_map, wi.tile * C * 2, (int)((long)wi.b * Cfg::N1 + r0));
           }
         }
@@ -486,83 +501,88 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
     if (wi.pass < 0) break;
     FB_TRACE(1);
     if (a.trace && blockIdx.x == 0 && t == 0 && k < kTraceTiles) a.trace[((long)g * (GT / 32) * kTraceTiles + k) * kTracePhases + 7] = wi.pass;
-
-    // ---- staging (or global memory) -> registers; the staging buffer is free again as soon as every thread has
-    // its samples ----
     const V* ring_rows = a.scratch + (size_t)wi.slot * N + (size_t)wi.tile * C * N2;   // pass 2: the tile's rows
-    Tile f;
-    if constexpr (Cfg::DIRECT) Math::load(f, wi.pass, t, wi.pass == 1 ? a.in + (size_t)wi.b * N + (size_t)wi.tile * C : ring_rows);
-    else Math::load(f, wi.pass, t, stage_g);
-    mbar_arrive(&ctl->empty);
-    if constexpr (!Cfg::DIRECT) {
-      if (wi.pass == 2) {
+
+    // One tile, from its samples to its stores; the whole group takes the same branch (wi is the group's item), so
+    // the named barriers inside are reached by all of its threads.  P = Math::Pass<1> or Pass<2>.
+    auto tile_body = [&](auto pass_tag) FB_LAMBDA {
+      constexpr int PASS = decltype(pass_tag)::value;
+      using P = typename Math::template Pass<PASS>;
+      constexpr uint32_t TILE_BYTES = PASS == 1 ? Cfg::TILE1_BYTES : Cfg::TILE2_BYTES;
+      // ---- staging (or global memory) -> registers; the staging buffer is free again as soon as every thread has
+      // its samples ----
+      typename P::Tile f;
+      if constexpr (Cfg::DIRECT) P::load(f, t, PASS == 1 ? a.in + (size_t)wi.b * N + (size_t)wi.tile * C : ring_rows);
+      else P::load(f, t, stage_g);
+      mbar_arrive(&ctl->empty);
+      if constexpr (!Cfg::DIRECT && PASS == 2) {
         // The intermediate rows this tile just consumed are dead: drop them from L2 instead of letting the
         // cache write them back to HBM later (measured: without this ~80% of the intermediate is written
         // back at RING = 8; the slot is completely rewritten before it is read again).
         const unsigned char* rows = reinterpret_cast<const unsigned char*>(ring_rows);
-        for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
+        for (uint32_t o = (uint32_t)t * 128u; o < TILE_BYTES; o += (uint32_t)GT * 128u)
           asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
         // the last warp of the group to have pulled its samples reports the ring slot as consumed by this
         // tile -- promptly and from the consumer side (a lazy report by the producer could deadlock it
         // against its own dependency wait)
         if ((t & 31) == 0 && atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
       }
-    }
-    FB_TRACE(2);
+      FB_TRACE(2);
 
-    Math::stage_a(f, wi.pass, t, twa);
-    if constexpr (Cfg::DIRECT) {
-      // same report with direct loads: stage A has consumed every register the warp loaded, so its global loads
-      // have completed
-      if (wi.pass == 2 && (t & 31) == 0 && atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
-    }
+      P::stage_a(f, t, PASS == 1 ? twa1 : twa2);
+      if constexpr (Cfg::DIRECT && PASS == 2) {
+        // same report with direct loads: stage A has consumed every register the warp loaded, so its global loads
+        // have completed
+        if ((t & 31) == 0 && atomicAdd(&ctl->loaded, 1) == GT / 32 - 1) { ctl->loaded = 0; atomicAdd(&done2[wi.b], 1u); }
+      }
 
-    // ---- exchange through the shared buffer (under the CTA-wide lock when the groups share one) ----------------
-    if (kLocked && t == 0) {
-      unsigned spins = 0;
-      while (atomicCAS(lock, 0, 1) != 0) if (++spins > (1u << 26)) __trap();
-    }
-    FB_TRACE(3);
-    group_sync(bar_id, GT);
-    if constexpr (Cfg::DIRECT) {
-      if (wi.pass == 2) {
+      // ---- exchange through the shared buffer (under the CTA-wide lock when the groups share one) --------------
+      if (kLocked && t == 0) {
+        unsigned spins = 0;
+        while (atomicCAS(lock, 0, 1) != 0) if (++spins > (1u << 26)) __trap();
+      }
+      FB_TRACE(3);
+      group_sync(bar_id, GT);
+      if constexpr (Cfg::DIRECT && PASS == 2) {
         // every warp of the group is past stage A, i.e. all loads of the tile have completed: drop its rows from L2
         const unsigned char* rows = reinterpret_cast<const unsigned char*>(ring_rows);
-        for (uint32_t o = (uint32_t)t * 128u; o < Cfg::TILE_BYTES; o += (uint32_t)GT * 128u)
+        for (uint32_t o = (uint32_t)t * 128u; o < TILE_BYTES; o += (uint32_t)GT * 128u)
           asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + o) : "memory");
       }
-    }
-    Math::scatter(f, wi.pass, t, exch);
-    FB_TRACE(4);
-    group_sync(bar_id, GT);
-    Math::gather(f, wi.pass, t, exch);
-    if constexpr (kLocked) {
+      P::scatter(f, t, exch);
+      FB_TRACE(4);
       group_sync(bar_id, GT);
-      if (t == 0) { __threadfence_block(); atomicExch(lock, 0); }
-    }
-    FB_TRACE(5);
-
-    // ---- stage B and the stores ---------------------------------------------------------------------------------
-    f.stage_b();
-    if (wi.pass == 1) {
-      const V* tb = tab_g + (size_t)(k_p1 & 1) * Cfg::TAB_ELEMS;
-      ++k_p1;
-      Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb);
-      // report "stores issued"; the last warp of the group hands the tile to the signaller warp
-      __syncwarp();
-      if ((t & 31) == 0 && atom_add_acq_rel_cta_shared(&ctl->stored_warps, 1u) == GT / 32 - 1) {
-        ctl->stored_warps = 0;
-        for (unsigned spins = 0; k_p1 - ld_acquire_cta_shared(&ctl->acked) > (unsigned)kStoreRing; ++spins) {
-          if (spins > (1u << 24)) __trap();   // the signaller is more than kStoreRing tiles behind: wait
-          __nanosleep(100);
-        }
-        ctl->store_b[(k_p1 - 1) % kStoreRing] = wi.b;
-        st_release_cta_shared(&ctl->stored_seq, k_p1);
+      P::gather(f, t, exch);
+      if constexpr (kLocked) {
+        group_sync(bar_id, GT);
+        if (t == 0) { __threadfence_block(); atomicExch(lock, 0); }
       }
-    } else {
-      Math::store2(f, t, a.out + (size_t)wi.b * N, wi.tile, a.do_scale != 0, a.scale);
-    }
-    FB_TRACE(6);
+      FB_TRACE(5);
+
+      // ---- stage B and the stores -------------------------------------------------------------------------------
+      f.stage_b();
+      if constexpr (PASS == 1) {
+        const V* tb = tab_g + (size_t)(k_p1 & 1) * Cfg::TAB_ELEMS;
+        ++k_p1;
+        Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb);
+        // report "stores issued"; the last warp of the group hands the tile to the signaller warp
+        __syncwarp();
+        if ((t & 31) == 0 && atom_add_acq_rel_cta_shared(&ctl->stored_warps, 1u) == GT / 32 - 1) {
+          ctl->stored_warps = 0;
+          for (unsigned spins = 0; k_p1 - ld_acquire_cta_shared(&ctl->acked) > (unsigned)kStoreRing; ++spins) {
+            if (spins > (1u << 24)) __trap();   // the signaller is more than kStoreRing tiles behind: wait
+            __nanosleep(100);
+          }
+          ctl->store_b[(k_p1 - 1) % kStoreRing] = wi.b;
+          st_release_cta_shared(&ctl->stored_seq, k_p1);
+        }
+      } else {
+        Math::store2(f, t, a.out + (size_t)wi.b * N, wi.tile, a.do_scale != 0, a.scale);
+      }
+      FB_TRACE(6);
+    };
+    if (wi.pass == 1) tile_body(std::integral_constant<int, 1>{});
+    else tile_body(std::integral_constant<int, 2>{});
   }
   group_sync(bar_id, GT);
   if (t == 0) st_release_cta_shared(&ctl->finished, 1u);

@@ -124,7 +124,7 @@ class Plan {
 
   // kOnChip / kTwoPass: see onchip.cu / twopass.cu
   size_t n1_ = 0, n2_ = 0;
-  DeviceBuffer tw_a_, tw_b_, tw2_, tw_f_;   // tw_f_: stage twiddles of the persistent kernel's register tile
+  DeviceBuffer tw_a_, tw_b_, tw2_, tw_f_, tw_f2_;   // tw_f_, tw_f2_: stage twiddles of the persistent kernel's two register tiles
   const void* fast_ops_ = nullptr;   // TwoPassOps<T> / OnChipOps<T> of the selected kernel family
   size_t chunk_ = 0;                 // transforms per L2-resident chunk (two-pass)
   const void* fused_ops_ = nullptr;  // FusedOps<T>: persistent single-launch variant

@@ -58,7 +58,7 @@ int env_int(const char* name, int dflt) {
 
 template <typename T> struct FusedOps {
   size_t n1, n2;
-  int ra, rb, tile_c;
+  int ra, rb, ra2, rb2, tile_c;   // register tiles of pass 1 (ra x rb) and pass 2 (ra2 x rb2)
   size_t smem_bytes;
   int default_ring, default_lag;
   bool base_pcol;   // layout of the factored base table this configuration reads (tables.cuh)
@@ -96,7 +96,7 @@ template <class Cfg> struct FusedImpl {
     return cudaGetLastError();
   }
   static const FusedOps<T>* ops(int ring, int lag) {
-    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::RA, Cfg::RB, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
+    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::RA, Cfg::RB, Cfg::RA2, Cfg::RB2, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
                                   true, &prepare, &launch};
     return &o;
   }
@@ -127,6 +127,23 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
     if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<float, 16, 8, 8, 8, 8, true, 8>>::ops(512, 256);
     return FusedImpl<fused::FusedCfg<float, 16, 8, 8, 8, 8, false, 8>>::ops(512, 256);
   }
+  // Odd powers of two: N1 x 2 N1 with a different register tile per pass, same threads per FFT in both
+  // (template arguments: <T, RA, C, G, PAD1, EXB, DIRECT, RB, RA2, RB2, E1, E2>).  Ring = 64 MB / transform size.
+  if (n == ((size_t)1 << 17)) {   // 256 (16 x 16, 16 per thread) x 512 (32 x 16, 32 per thread): three 128-thread groups
+    if (env_int("FOURIER_B200_CFG", 0) == 1)
+      return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true, 16, 32, 16, 16, 32>>::ops(64, 32);
+    return FusedImpl<fused::FusedCfg<float, 16, 8, 3, 8, 3, false, 16, 32, 16, 16, 32>>::ops(64, 32);
+  }
+  if (n == ((size_t)1 << 15)) {   // 128 (16 x 8, 16 per thread) x 256 (16 x 16, 32 per thread): six 64-thread groups
+    if (env_int("FOURIER_B200_CFG", 0) == 1)
+      return FusedImpl<fused::FusedCfg<float, 16, 8, 8, 8, 8, true, 8, 16, 16, 16, 32>>::ops(256, 128);
+    return FusedImpl<fused::FusedCfg<float, 16, 8, 6, 8, 6, false, 8, 16, 16, 16, 32>>::ops(256, 128);
+  }
+  if (n == ((size_t)1 << 13)) {   // 64 (8 x 8, 8 per thread) x 128 (16 x 8, 16 per thread): eight 64-thread groups
+    if (env_int("FOURIER_B200_CFG", 0) == 1)
+      return FusedImpl<fused::FusedCfg<float, 8, 8, 8, 8, 8, true, 8, 16, 8, 8, 16>>::ops(1024, 512);
+    return FusedImpl<fused::FusedCfg<float, 8, 8, 8, 8, 8, false, 8, 16, 8, 8, 16>>::ops(1024, 512);
+  }
   return nullptr;
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
@@ -139,6 +156,9 @@ template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
     // 128 x 128 with 16 x 8 register tiles: eight 64-thread groups loading directly, or five with TMA staging
     if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<double, 16, 8, 5, 4, 5, false, 8>>::ops(256, 128);
     return FusedImpl<fused::FusedCfg<double, 16, 8, 8, 4, 8, true, 8>>::ops(256, 128);
+  }
+  if (n == ((size_t)1 << 13)) {   // 64 (8 x 8) x 128 (16 x 8): eight 64-thread groups loading directly
+    return FusedImpl<fused::FusedCfg<double, 8, 8, 8, 4, 8, true, 8, 16, 8, 8, 16>>::ops(512, 256);
   }
   return nullptr;
 }
@@ -175,6 +195,7 @@ cudaError_t Plan<T>::init_twopass() {
     if (f && f->prepare() == cudaSuccess) {
       // the persistent kernel has its own split and register tile (the tile kernels above stay as its fallback)
       FB_CHECK((upload_vec<T, TwPair<T>>(tw_f_, make_twa<T>(f->ra, f->rb))));
+      FB_CHECK((upload_vec<T, TwPair<T>>(tw_f2_, make_twa<T>(f->ra2, f->rb2))));
       // factored inter-pass twiddles, contiguous per pass-1 tile of `tile_c` columns:
       //   tbase[tile][col][p] = w_N^{n2*p},  tstep[tile][r][col] = w_N^{R*n2*r},  n2 = tile*tile_c + col
       std::vector<cpx<T>> tb, ts;
@@ -214,6 +235,7 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
     fused::FusedArgs<T> a;
     a.in = in; a.out = out; a.scratch = (C*)work_.data();
     a.twa = (const TwPair<T>*)tw_f_.data();
+    a.twa2 = (const TwPair<T>*)tw_f2_.data();
     a.tbase = (const C*)tbase_.data(); a.tstep = (const C*)tstep_.data();
     a.counters = (unsigned*)counters_.data();
     a.trace = nullptr;

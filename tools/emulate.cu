@@ -19,6 +19,9 @@
 #ifndef FB_PAD16
 #define FB_PAD16 8
 #endif
+#ifndef FB_PADX
+#define FB_PADX 8
+#endif
 using namespace fb200;
 using namespace fb200::twopass;
 
@@ -272,12 +275,12 @@ static int check_fused(const char* name, double tol) {
   using T = typename Cfg::T;
   using V = cpx<T>;
   constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
-  constexpr int C = Cfg::C, R = Cfg::R, GT = Cfg::GT;
-  printf("%s: persistent-kernel arithmetic, N=%ld, blocked intermediate%s\n", name, N, Cfg::DIRECT ? ", direct loads" : "");
-  report_conflicts<typename Cfg::template Tile<true>, typename Cfg::Lay1, kMapCF>("pass 1");
-  report_conflicts<typename Cfg::template Tile<true>, typename Cfg::Lay2, fused::FusedMath<Cfg, true>::kMap2>("pass 2");
+  constexpr int C = Cfg::C, GT = Cfg::GT;
+  printf("%s: persistent-kernel arithmetic, N=%ld = %ld x %ld, blocked intermediate%s\n", name, N, N1, N2, Cfg::DIRECT ? ", direct loads" : "");
+  report_conflicts<typename Cfg::template Tile1<true>, typename Cfg::Lay1, kMapCF>("pass 1");
+  report_conflicts<typename Cfg::template Tile2<true>, typename Cfg::Lay2, fused::FusedMath<Cfg, true>::kMap2>("pass 2");
   {  // staging reads of pass 2 (the other staging / table reads are contiguous by construction)
-    using Tile = typename Cfg::template Tile<true>;
+    using Tile = typename Cfg::template Tile2<true>;
     int worst = 1;
     for (int warp = 0; warp < GT / 32; ++warp)
       for (int i = 0; i < Tile::RA; ++i) {
@@ -295,7 +298,8 @@ static int check_fused(const char* name, double tol) {
   }
   {  // LSU cost model of the two accesses the blocked layout changes: 128-byte lines touched by one warp-wide
      // pass-1 store, and different stage twiddles one warp loads in pass 2 (identical addresses broadcast)
-    using Tile = typename Cfg::template Tile<true>;
+    using Tile = typename Cfg::template Tile1<true>;
+    using TileB = typename Cfg::template Tile2<true>;
     constexpr int M = fused::FusedMath<Cfg, true>::kMap2;
     long lines = 0, twiddles = 0;
     for (int warp = 0; warp < GT / 32; ++warp) {
@@ -304,7 +308,7 @@ static int check_fused(const char* name, double tol) {
         const int t = warp * 32 + l;
         const long col = Tile::template col_of<kMapCF>(t), p = Tile::template u_of<kMapCF>(t);
         const long e = (p >> 3) * (N2 * 8) + (p & 7) * 8 + col;   // output r = 0
-        const long line = e * (long)sizeof(V) / 128, tw = Tile::template u_of<M>(t);
+        const long line = e * (long)sizeof(V) / 128, tw = TileB::template u_of<M>(t);
         if (std::find(seen_l.begin(), seen_l.end(), line) == seen_l.end()) seen_l.push_back(line);
         if (std::find(seen_t.begin(), seen_t.end(), tw) == seen_t.end()) seen_t.push_back(tw);
       }
@@ -314,43 +318,48 @@ static int check_fused(const char* name, double tol) {
     printf("  per warp: %.1f lines of 128 B per pass-1 store instruction (%d B stored), %.1f different pass-2 stage twiddles\n",
            (double)lines / (GT / 32), 32 * (int)sizeof(V), (double)twiddles / (GT / 32));
   }
-  auto twa_pairs = make_twa<T>(Cfg::RA, Cfg::RB);
-  std::vector<TwPair<T>> twa(twa_pairs.size());     // the kernel re-lays the table out in 8-byte planes
-  for (int i = 0; i < (int)twa_pairs.size(); ++i) fused::FusedMath<Cfg, true>::relayout_twa(twa.data(), twa_pairs.data(), i);
+  auto twa_pairs = make_twa<T>(Cfg::RA, Cfg::RB), twa2_pairs = make_twa<T>(Cfg::RA2, Cfg::RB2);
+  std::vector<TwPair<T>> twa(twa_pairs.size()), twa2(twa2_pairs.size());     // the kernel re-lays the tables out in 8-byte planes
+  for (int i = 0; i < (int)twa_pairs.size(); ++i) fused::FusedMath<Cfg, true>::relayout_twa(twa.data(), twa_pairs.data(), i, (int)twa_pairs.size());
+  for (int i = 0; i < (int)twa2_pairs.size(); ++i) fused::FusedMath<Cfg, true>::relayout_twa(twa2.data(), twa2_pairs.data(), i, (int)twa2_pairs.size());
   std::vector<V> tbase, tstep;
   make_factored_twiddles<T>((size_t)N, (size_t)N2, Cfg::RA, Cfg::RB, C, tbase, tstep, true);
   int bad = 0;
   for (int fwd = 1; fwd >= 0; --fwd) {
-    std::vector<V> x(N), scratch(N), out(N), staging((size_t)C * Cfg::L), tab((size_t)Cfg::TAB_ELEMS);
+    std::vector<V> x(N), scratch(N), out(N), staging((size_t)C * std::max(N1, N2)), tab((size_t)Cfg::TAB_ELEMS);
     std::vector<V> exch(Cfg::EX_ELEMS);
     fill<T>(x, 41 + fwd);
     const T scale = (T)0.5;
-    auto run_tile = [&](auto fwd_tag, int pass, int tile) {
+    auto run_tile = [&](auto fwd_tag, auto pass_tag, int tile) {
       constexpr bool FWD = decltype(fwd_tag)::value;
+      constexpr int PASS = decltype(pass_tag)::value;
       using Math = fused::FusedMath<Cfg, FWD>;
-      std::vector<typename Math::Tile> thr(GT);
+      using P = typename Math::template Pass<PASS>;
+      std::vector<typename P::Tile> thr(GT);
       // direct mode: the threads read global memory themselves (same pointers as the kernel computes)
-      const V* src = !Cfg::DIRECT ? staging.data() : pass == 1 ? x.data() + (size_t)tile * C
+      const V* src = !Cfg::DIRECT ? staging.data() : PASS == 1 ? x.data() + (size_t)tile * C
                                                                 : scratch.data() + (size_t)tile * C * N2;
-      for (int t = 0; t < GT; ++t) { Math::load(thr[t], pass, t, src); Math::stage_a(thr[t], pass, t, twa.data()); }
-      for (int t = 0; t < GT; ++t) Math::scatter(thr[t], pass, t, exch.data());
+      for (int t = 0; t < GT; ++t) { P::load(thr[t], t, src); P::stage_a(thr[t], t, PASS == 1 ? twa.data() : twa2.data()); }
+      for (int t = 0; t < GT; ++t) P::scatter(thr[t], t, exch.data());
       for (int t = 0; t < GT; ++t) {
-        Math::gather(thr[t], pass, t, exch.data());
+        P::gather(thr[t], t, exch.data());
         thr[t].stage_b();
-        if (pass == 1) Math::store1(thr[t], t, scratch.data(), tile, tab.data());
+        if constexpr (PASS == 1) Math::store1(thr[t], t, scratch.data(), tile, tab.data());
         else Math::store2(thr[t], t, out.data(), tile, true, scale);
       }
     };
+    using One = std::integral_constant<int, 1>;
+    using Two = std::integral_constant<int, 2>;
     for (int tile = 0; tile < Cfg::T1; ++tile) {        // pass 1: TMA box = rows n1, columns tile*C .. +C
       for (long r = 0; r < N1; ++r)
         for (int c = 0; c < C; ++c) staging[r * C + c] = x[r * N2 + (long)tile * C + c];
       for (int i = 0; i < Cfg::TAB_BASE; ++i) tab[i] = tbase[(size_t)tile * Cfg::TAB_BASE + i];
       for (int i = 0; i < Cfg::TAB_STEP; ++i) tab[Cfg::TAB_BASE + i] = tstep[(size_t)tile * Cfg::TAB_STEP + i];
-      if (fwd) run_tile(std::true_type{}, 1, tile); else run_tile(std::false_type{}, 1, tile);
+      if (fwd) run_tile(std::true_type{}, One{}, tile); else run_tile(std::false_type{}, One{}, tile);
     }
     for (int tile = 0; tile < Cfg::T2; ++tile) {        // pass 2: bulk copy of C*N2 contiguous samples
       for (long i = 0; i < (long)C * N2; ++i) staging[i] = scratch[(size_t)tile * C * N2 + i];
-      if (fwd) run_tile(std::true_type{}, 2, tile); else run_tile(std::false_type{}, 2, tile);
+      if (fwd) run_tile(std::true_type{}, Two{}, tile); else run_tile(std::false_type{}, Two{}, tile);
     }
     std::vector<double> re(N), im(N);
     for (long i = 0; i < N; ++i) { re[i] = x[i].x; im[i] = x[i].y; }
@@ -551,6 +560,11 @@ int main() {
   bad += check_fused<fused::FusedCfg<double, 16, 8, 3, 4, 3>>("fused f64 2^16", 5e-15);
   bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 8, 2, true>>("fused f32 2^20", 2e-6);
   bad += check_fused<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>("fused f64 2^16", 5e-15);
+  // <T, RA, C, G, PAD1, EXB, DIRECT, RB, RA2, RB2, E1, E2>
+  bad += check_fused<fused::FusedCfg<float, 16, 8, 6, 8, 6, false, 8, 16, 16, 16, 32>>("fused f32 2^15", 2e-6);
+  bad += check_fused<fused::FusedCfg<float, 8, 8, 8, 8, 8, false, 8, 16, 8, 8, 16>>("fused f32 2^13", 2e-6);
+  bad += check_fused<fused::FusedCfg<float, 16, 8, 3, 8, 3, false, 16, 32, 16, 16, 32>>("fused f32 2^17", 2e-6);
+  bad += check_fused<fused::FusedCfg<double, 8, 8, 8, 4, 8, true, 8, 16, 8, 8, 16>>("fused f64 2^13", 5e-15);
   bad += check_fused<fused::FusedCfg<float, 32, 8, 3, 8, 3, false, 16>>("fused f32 2^18", 2e-6);
   bad += check_fused<fused::FusedCfg<float, 16, 8, 8, 8, 8, false, 8>>("fused f32 2^14", 2e-6);
   bad += check_fused<fused::FusedCfg<double, 16, 8, 8, 4, 8, true, 8>>("fused f64 2^14", 5e-15);
