@@ -194,6 +194,8 @@ struct FusedCfg {
   static_assert(C_ == 8 && RB_ % 8 == 0 && RB2_ % 8 == 0, "the blocked intermediate needs 8-column tiles");
   static constexpr int GT = Tile1<true>::THREADS;     // threads per group
   static constexpr int CONSUMERS = G * GT;
+  // setmaxnreg is a warpgroup-wide instruction: consumers and producers must not share a group of four warps
+  static_assert(CONSUMERS % 128 == 0, "the consumer threads must fill whole warpgroups");
   static constexpr int AUX = ((G + 1 + 3) / 4) * 128;  // G producer warps + 1 signaller warp, in whole warpgroups
   static constexpr int THREADS = CONSUMERS + AUX;
   // Register budget.  Registers are handed out per 4 warps, so a 17th warp costs as much as 4; the

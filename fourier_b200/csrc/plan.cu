@@ -112,6 +112,7 @@ struct DeviceGuard {
 constexpr size_t kScratchTargetBytes = (size_t)512 << 20;  // per scratch buffer on the general path
 constexpr size_t kHostChunkBytes = (size_t)64 << 20;       // host-pointer pipeline granule
 constexpr size_t kHostSmallBytes = (size_t)1 << 20;        // below this a host call takes the single-stream latency path
+constexpr size_t kHostZeroCopyBytes = (size_t)64 << 10;    // below this the kernel reads / writes mapped host memory itself
 
 }  // namespace
 
@@ -160,6 +161,8 @@ Plan<T>::~Plan() {
     if (s) cudaStreamDestroy(s);
   for (auto& e : events_)
     if (e) cudaEventDestroy(e);
+  if (zc_in_) cudaFreeHost(zc_in_);
+  if (zc_out_) cudaFreeHost(zc_out_);
 }
 
 template <typename T>
@@ -377,6 +380,23 @@ cudaError_t Plan<T>::exec_host(const C* in, C* out, size_t batch, int code) {
     // Latency path (the reference ABI's single small transform, fourier-ffi/src/lib.rs:46-59): nothing to
     // pipeline, so one stream, no events, one synchronisation: H2D, kernel(s), D2H back to back.
     cudaStream_t s = streams_[1];
+    if (batch * bytes_per <= kHostZeroCopyBytes && !std::getenv("FOURIER_B200_NO_ZEROCOPY")) {
+      // Smallest calls: the two DMA copies cost more than the transform.  The kernels read the input from and write
+      // the result to a pinned, device-mapped bounce buffer over PCIe themselves (one launch, one synchronisation;
+      // the CPU copies 2 x <= 64 KB).  Measured: 24 -> ~12 us per 1024-point call (profiles/r02_latency.txt).
+      if (!zc_in_) {
+        FB_CHECK(cudaHostAlloc(&zc_in_, kHostZeroCopyBytes, cudaHostAllocMapped));
+        FB_CHECK(cudaHostAlloc(&zc_out_, kHostZeroCopyBytes, cudaHostAllocMapped));
+      }
+      std::memcpy(zc_in_, in, batch * bytes_per);
+      void *din = nullptr, *dout = nullptr;
+      FB_CHECK(cudaHostGetDevicePointer(&din, zc_in_, 0));
+      FB_CHECK(cudaHostGetDevicePointer(&dout, zc_out_, 0));
+      FB_CHECK(exec_device((const C*)din, (C*)dout, batch, code, s));
+      FB_CHECK(cudaStreamSynchronize(s));
+      std::memcpy(out, zc_out_, batch * bytes_per);
+      return cudaSuccess;
+    }
     FB_CHECK(stage_[0].reserve(std::max(batch * bytes_per, kHostSmallBytes)));
     C* dev = (C*)stage_[0].data();
     FB_CHECK(cudaMemcpyAsync(dev, in, batch * bytes_per, cudaMemcpyHostToDevice, s));

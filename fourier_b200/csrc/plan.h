@@ -147,6 +147,8 @@ class Plan {
   cudaStream_t streams_[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t events_[9] = {};
   cudaError_t host_resources();   // streams and events of the host-pointer path, created once
+  void* zc_in_ = nullptr;         // pinned, device-mapped bounce buffers of the smallest host calls (64 KB each)
+  void* zc_out_ = nullptr;
 };
 
 // thread-local error text for the C ABI

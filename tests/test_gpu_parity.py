@@ -310,12 +310,13 @@ def test_misaligned_device_pointer_is_refused():
 def test_kernel_names_follow_the_path():
     names = {(r, n): create(r, n).kernel_name() for r, n in
              [("f32", 1 << 20), ("f64", 1 << 16), ("f32", 1 << 16), ("f32", 1024), ("f32", 1009), ("f32", 729),
-              ("f64", 1009), ("f32", 1 << 15), ("f32", 3 ** 9)]}
+              ("f64", 1009), ("f32", 1 << 19), ("f32", 3 ** 9), ("f32", 1 << 15)]}
     assert "fused_twopass_kernel" in names[("f32", 1 << 20)] and "fused_twopass_kernel" in names[("f64", 1 << 16)]
     assert "fused_twopass_kernel" in names[("f32", 1 << 16)]
     assert "onchip_fft_kernel" in names[("f32", 1024)] and "bluestein_fused_kernel" in names[("f32", 1009)]
     assert "cta_fft_kernel" in names[("f32", 729)] and "chirp" in names[("f64", 1009)]
-    assert "tile_kernel" in names[("f32", 1 << 15)] and "stockham_stage_kernel" in names[("f32", 3 ** 9)]
+    assert "tile_kernel" in names[("f32", 1 << 19)] and "stockham_stage_kernel" in names[("f32", 3 ** 9)]
+    assert "fused_twopass_kernel" in names[("f32", 1 << 15)]
 
 
 def test_error_conventions():
