@@ -158,7 +158,7 @@ template <typename T> struct FusedArgs {
   long long* trace;           // optional phase timestamps of CTA 0 (debugging / DESIGN.md timeline), else nullptr
 };
 
-// Configuration: N = (R*R)^2, tiles of C = 8 FFTs, G consumer groups per CTA, EXB exchange buffers (group g uses
+// Configuration: N = N1 * N2 (two register-tile lengths, see RB_ / RA2_ ... below), tiles of C = 8 FFTs, G consumer groups per CTA, EXB exchange buffers (group g uses
 // g % EXB, under a lock when shared); the staging buffer is released as soon as the samples are in registers.
 // The intermediate is stored in 8 x 8 blocks [k1 / 8][n2 / 8][k1 % 8][n2 % 8]: a pass-1 tile writes 256-byte runs (a
 // warp's store = 4 consecutive k1 x 8 columns; row-major A[k1][n2] gave four 64-byte pieces and twice the LSU
