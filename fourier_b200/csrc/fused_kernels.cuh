@@ -173,25 +173,30 @@ template <typename T> struct FusedArgs {
 //          (two 256-thread groups: -12 %), same profile file.
 // RB_: second radix of the register tile when the tile length L = R_ * RB_ is not a square (L = 128 = 16 x 8,
 //      512 = 32 x 16): N = L^2 = 2^14, 2^18.
+// C1_: columns per pass-1 tile (8, or 16 = two 8 x 8 block columns: then the strided input is read in 128-byte pieces
+//      and a 512-point pass-1 tile has as many threads as a 1024-point pass-2 tile: 2^19 = 512 x 1024).
+// TABG_: the factored-twiddle tables of a pass-1 tile are read from global memory (L2-resident, 6 KB per tile) instead
+//      of travelling into shared memory with the tile: for the one configuration whose shared memory is full (2^19).
 // RA2_, RB2_, E1_, E2_: a different register tile for pass 2 (N2 = RA2_ * RB2_ != N1 = R_ * RB_: the odd powers of
 //      two, e.g. 2^15 = 128 x 256); E1_ / E2_ samples per thread chosen so that both tiles have the same number of
 //      threads per FFT (TP = N1 / E1 = N2 / E2), i.e. the same group size.
 template <typename T_, int R_, int C_, int G_, int PAD1_, int EXB_ = 1, bool DIRECT_ = false, int RB_ = R_,
-          int RA2_ = R_, int RB2_ = RB_, int E1_ = (R_ > RB_ ? R_ : RB_), int E2_ = (RA2_ > RB2_ ? RA2_ : RB2_)>
+          int RA2_ = R_, int RB2_ = RB_, int E1_ = (R_ > RB_ ? R_ : RB_), int E2_ = (RA2_ > RB2_ ? RA2_ : RB2_),
+          int C1_ = C_, bool TABG_ = false>
 struct FusedCfg {
   using T = T_;
-  static constexpr bool DIRECT = DIRECT_;
+  static constexpr bool DIRECT = DIRECT_, TABG = TABG_;
   static_assert(!DIRECT_ || EXB_ == G_, "direct loads: one exchange buffer per group");
-  static constexpr int RA = R_, RB = RB_, RA2 = RA2_, RB2 = RB2_, C = C_, G = G_, EXB = EXB_;
+  static constexpr int RA = R_, RB = RB_, RA2 = RA2_, RB2 = RB2_, C = C_, C1 = C1_, G = G_, EXB = EXB_;
   static constexpr long N1 = (long)RA * RB, N2 = (long)RA2 * RB2, N = N1 * N2;
-  template <bool FWD> using Tile1 = TileFFT<T, RA, RB, E1_, C, FWD>;     // pass 1: C columns, FFT length N1
+  template <bool FWD> using Tile1 = TileFFT<T, RA, RB, E1_, C1, FWD>;    // pass 1: C1 columns, FFT length N1
   template <bool FWD> using Tile2 = TileFFT<T, RA2, RB2, E2_, C, FWD>;   // pass 2: C rows, FFT length N2
   static_assert(Tile1<true>::THREADS == Tile2<true>::THREADS, "both register tiles must use the same group size");
-  using Lay1 = ExLayout<RA * C + PAD1_, C, 1>;                     // pass 1: scatter and gather col-fast
+  using Lay1 = ExLayout<RA * C1 + PAD1_, C1, 1>;                   // pass 1: scatter and gather col-fast
   // pass 2: scatter block-fast (row stride = 2 mod 16 for 8-byte, odd for 16-byte elements: conflict-free for
   // lanes = 8 positions x 4 FFTs), gather col-fast
   using Lay2 = ExLayout<RA2 * C + (sizeof(T_) == 4 ? 2 : 1), C, 1>;
-  static_assert(C_ == 8 && RB_ % 8 == 0 && RB2_ % 8 == 0, "the blocked intermediate needs 8-column tiles");
+  static_assert(C_ == 8 && (C1_ == 8 || C1_ == 16) && RB_ % 8 == 0 && RB2_ % 8 == 0, "the blocked intermediate: 8 x 8 blocks");
   static constexpr int GT = Tile1<true>::THREADS;     // threads per group
   static constexpr int CONSUMERS = G * GT;
   // setmaxnreg is a warpgroup-wide instruction: consumers and producers must not share a group of four warps
@@ -205,11 +210,11 @@ struct FusedCfg {
   static constexpr int REGS_PRODUCER = 24;
   static constexpr int REGS_CONSUMER_RAW = ((LAUNCH_REGS * THREADS - REGS_PRODUCER * AUX) / CONSUMERS / 8) * 8;
   static constexpr int REGS_CONSUMER = REGS_CONSUMER_RAW > 232 ? 232 : REGS_CONSUMER_RAW;
-  static constexpr int T1 = (int)(N2 / C), T2 = (int)(N1 / C);
-  static constexpr uint32_t TILE1_BYTES = (uint32_t)(sizeof(cpx<T>) * C * N1), TILE2_BYTES = (uint32_t)(sizeof(cpx<T>) * C * N2);
-  static constexpr int TAB_BASE = C * RA, TAB_STEP = C * RB, TAB_ELEMS = TAB_BASE + TAB_STEP;   // [base | step] of a tile
+  static constexpr int T1 = (int)(N2 / C1), T2 = (int)(N1 / C);
+  static constexpr uint32_t TILE1_BYTES = (uint32_t)(sizeof(cpx<T>) * C1 * N1), TILE2_BYTES = (uint32_t)(sizeof(cpx<T>) * C * N2);
+  static constexpr int TAB_BASE = C1 * RA, TAB_STEP = C1 * RB, TAB_ELEMS = TAB_BASE + TAB_STEP;   // [base | step] of a tile
   static constexpr uint32_t TAB_BASE_BYTES = (uint32_t)(sizeof(cpx<T>) * TAB_BASE), TAB_STEP_BYTES = (uint32_t)(sizeof(cpx<T>) * TAB_STEP);
-  static constexpr uint32_t TAB_BYTES = TAB_BASE_BYTES + TAB_STEP_BYTES;
+  static constexpr uint32_t TAB_BYTES = TABG ? 0 : TAB_BASE_BYTES + TAB_STEP_BYTES;   // travelling with a tile
   static constexpr int EX1 = Tile1<true>::template smem_elems<Lay1>(), EX2 = Tile2<true>::template smem_elems<Lay2>();
   static constexpr int EX_ELEMS = EX1 > EX2 ? EX1 : EX2;
   static constexpr size_t EX_BYTES = ((sizeof(cpx<T>) * EX_ELEMS + 127) / 128) * 128;
@@ -256,6 +261,7 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   if constexpr (Cfg::DIRECT) {
     // nothing to stage, the consumers read global memory themselves; only the tile tables of a pass-1 tile travel
     if (wi.pass == 2) { mbar_arrive(&ctl->full); return; }
+    if constexpr (Cfg::TABG) { mbar_arrive(&ctl->full); return; }
     mbar_arrive_expect_tx(&ctl->full, Cfg::TAB_BYTES);
     bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE, Cfg::TAB_BASE_BYTES, &ctl->full);
     bulk_load(tab + Cfg::TAB_BASE, a.tstep + (size_t)wi.tile * Cfg::TAB_STEP, Cfg::TAB_STEP_BYTES, &ctl->full);
@@ -265,12 +271,14 @@ __device__ __forceinline__ void issue_tile(const WorkItem& wi, const CUtensorMap
   if (wi.pass == 1) {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE1_BYTES + Cfg::TAB_BYTES);
     constexpr int BOX = Cfg::BOX_ROWS;
-    const int x = wi.tile * C * 2;  // in scalars of T
+    const int x = wi.tile * Cfg::C1 * 2;  // in scalars of T
 #pragma unroll
     for (int r0 = 0; r0 < (int)Cfg::N1; r0 += BOX)
-      tma_load_2d_first(dst + (size_t)r0 * C, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), &ctl->full);
-    bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE, Cfg::TAB_BASE_BYTES, &ctl->full);
-    bulk_load(tab + Cfg::TAB_BASE, a.tstep + (size_t)wi.tile * Cfg::TAB_STEP, Cfg::TAB_STEP_BYTES, &ctl->full);
+      tma_load_2d_first(dst + (size_t)r0 * Cfg::C1, in_map, x, (int)((long)wi.b * Cfg::N1 + r0), &ctl->full);
+    if constexpr (!Cfg::TABG) {
+      bulk_load(tab, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE, Cfg::TAB_BASE_BYTES, &ctl->full);
+      bulk_load(tab + Cfg::TAB_BASE, a.tstep + (size_t)wi.tile * Cfg::TAB_STEP, Cfg::TAB_STEP_BYTES, &ctl->full);
+    }
   } else {
     mbar_arrive_expect_tx(&ctl->full, Cfg::TILE2_BYTES);
     const V* src = a.scratch + (size_t)d.slot * Cfg::N + (size_t)wi.tile * C * Cfg::N2;
@@ -313,7 +321,7 @@ template <class Cfg, bool FWD> struct FusedMath {
     using Tile = Tile1;
     static FB_HD void load(Tile& f, int t, const V* stage) {
       if constexpr (Cfg::DIRECT) f.template load<kMapCF, N2, 1, 1>(t, stage);
-      else f.template load<kMapCF, C, 1>(t, stage);
+      else f.template load<kMapCF, Cfg::C1, 1>(t, stage);
     }
     static FB_HD void stage_a(Tile& f, int t, const TwPair<T>* twa) { f.template stage_a<kMapCF, true>(t, twa); }
     static FB_HD void scatter(const Tile& f, int t, V* exch) { f.template scatter<kMapCF, typename Cfg::Lay1>(t, exch); }
@@ -337,8 +345,8 @@ template <class Cfg, bool FWD> struct FusedMath {
   static FB_HD void relayout_twa(void* planes, const TwPair<T>* src, int i, int pairs) {
     TwPlanes<T>::put(planes, pairs, i, src[i]);
   }
-  static FB_HD void store1(const Tile1& f, int t, V* slot_base, int tile, const V* tb) {
-    f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * 64, tb, tb + Cfg::TAB_BASE);
+  static FB_HD void store1(const Tile1& f, int t, V* slot_base, int tile, const V* tbase, const V* tstep) {
+    f.template store_factored<N2, 1, 2, N2 * 8, true>(t, slot_base + (size_t)tile * (8 * Cfg::C1), tbase, tstep);
   }
   static FB_HD void store2(const Tile2& f, int t, V* out_b, int tile, bool do_scale, T scale) {
     V* dst = out_b + (size_t)tile * C;
@@ -437,7 +445,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
           if (wi.pass == 1) {
 #pragma unroll
             for (int r0 = 0; r0 < (int)Cfg::N1; r0 += Cfg::BOX_ROWS)
-              tma_prefetch_2d(&in_map, wi.tile * C * 2, (int)((long)wi.b * Cfg::N1 + r0));
+              tma_prefetch_2d(&in_map, wi.tile * Cfg::C1 * 2, (int)((long)wi.b * Cfg::N1 + r0));
           }
         }
         FB_PTRACE(2);
@@ -514,7 +522,7 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       // ---- staging (or global memory) -> registers; the staging buffer is free again as soon as every thread has
       // its samples ----
       typename P::Tile f;
-      if constexpr (Cfg::DIRECT) P::load(f, t, PASS == 1 ? a.in + (size_t)wi.b * N + (size_t)wi.tile * C : ring_rows);
+      if constexpr (Cfg::DIRECT) P::load(f, t, PASS == 1 ? a.in + (size_t)wi.b * N + (size_t)wi.tile * Cfg::C1 : ring_rows);
       else P::load(f, t, stage_g);
       mbar_arrive(&ctl->empty);
       if constexpr (!Cfg::DIRECT && PASS == 2) {
@@ -566,7 +574,11 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       if constexpr (PASS == 1) {
         const V* tb = tab_g + (size_t)(k_p1 & 1) * Cfg::TAB_ELEMS;
         ++k_p1;
-        Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb);
+        if constexpr (Cfg::TABG)
+          Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE,
+                       a.tstep + (size_t)wi.tile * Cfg::TAB_STEP);
+        else
+          Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb, tb + Cfg::TAB_BASE);
         // report "stores issued"; the last warp of the group hands the tile to the signaller warp
         __syncwarp();
         if ((t & 31) == 0 && atom_add_acq_rel_cta_shared(&ctl->stored_warps, 1u) == GT / 32 - 1) {

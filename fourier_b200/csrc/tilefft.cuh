@@ -275,11 +275,13 @@ struct TileFFT {
   template <long KS, long CS, int HINT, long BLOCK_ROW = 0, bool BASE_PCOL = false>
   FB_HD void store_factored(int t, V* __restrict__ base, const V* sbase, const V* sstep) const {
     const int col = col_of<false>(t), u = u_of<false>(t);
-    static_assert(BLOCK_ROW == 0 || (C == 8 && RA % 8 == 0), "blocked intermediate: 8 columns per tile");
+    static_assert(BLOCK_ROW == 0 || ((C == 8 || C == 16) && RA % 8 == 0), "blocked intermediate: 8 or 16 columns per tile");
     static_for<0, NB>([&](auto Cc) FB_LAMBDA {
       constexpr int c = decltype(Cc)::value;
       const int p = u + TP * c;
-      const long off = BLOCK_ROW ? (long)(p >> 3) * BLOCK_ROW + (p & 7) * 8 + col : (long)col * CS + (long)p * KS;
+      // blocked: column block col / 8 (64 elements apart), row p % 8 of the block, column col % 8
+      const long off = BLOCK_ROW ? (long)(p >> 3) * BLOCK_ROW + (col >> 3) * 64 + (p & 7) * 8 + (col & 7)
+                                 : (long)col * CS + (long)p * KS;
       const V wb = BASE_PCOL ? sbase[p * C + col] : sbase[col * RA + p];
       static_for<0, RB>([&](auto Rr) FB_LAMBDA {
         constexpr int r = decltype(Rr)::value;

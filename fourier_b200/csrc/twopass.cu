@@ -58,7 +58,7 @@ int env_int(const char* name, int dflt) {
 
 template <typename T> struct FusedOps {
   size_t n1, n2;
-  int ra, rb, ra2, rb2, tile_c;   // register tiles of pass 1 (ra x rb) and pass 2 (ra2 x rb2)
+  int ra, rb, ra2, rb2, tile_c;   // register tiles of pass 1 (ra x rb) and pass 2 (ra2 x rb2); columns per pass-1 tile
   size_t smem_bytes;
   int default_ring, default_lag;
   bool base_pcol;   // layout of the factored base table this configuration reads (tables.cuh)
@@ -82,7 +82,7 @@ template <class Cfg> struct FusedImpl {
     CUtensorMap map;
     const cuuint64_t gdim[2] = {(cuuint64_t)(2 * Cfg::N2), (cuuint64_t)a.batch * (cuuint64_t)Cfg::N1};
     const cuuint64_t gstride[1] = {(cuuint64_t)(Cfg::N2 * sizeof(cpx<T>))};
-    const cuuint32_t box[2] = {(cuuint32_t)(2 * Cfg::C), (cuuint32_t)Cfg::BOX_ROWS};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * Cfg::C1), (cuuint32_t)Cfg::BOX_ROWS};
     const cuuint32_t estr[2] = {1, 1};
     const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
     if (enc(&map, dt, 2, (void*)a.in, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -96,7 +96,7 @@ template <class Cfg> struct FusedImpl {
     return cudaGetLastError();
   }
   static const FusedOps<T>* ops(int ring, int lag) {
-    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::RA, Cfg::RB, Cfg::RA2, Cfg::RB2, Cfg::C, Cfg::SMEM_BYTES, ring, lag,
+    static const FusedOps<T> o = {(size_t)Cfg::N1, (size_t)Cfg::N2, Cfg::RA, Cfg::RB, Cfg::RA2, Cfg::RB2, Cfg::C1, Cfg::SMEM_BYTES, ring, lag,
                                   true, &prepare, &launch};
     return &o;
   }
@@ -129,6 +129,9 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
   }
   // Odd powers of two: N1 x 2 N1 with a different register tile per pass, same threads per FFT in both
   // (template arguments: <T, RA, C, G, PAD1, EXB, DIRECT, RB, RA2, RB2, E1, E2>).  Ring = 64 MB / transform size.
+  if (n == ((size_t)1 << 19)) {   // 512 (32 x 16) x 1024 (32 x 32), 16-column pass-1 tiles: two 256-thread groups
+    return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 0, 1, false, 16, 32, 32, 32, 32, 16, true>>::ops(16, 8);
+  }
   if (n == ((size_t)1 << 17)) {   // 256 (16 x 16, 16 per thread) x 512 (32 x 16, 32 per thread): three 128-thread groups
     if (env_int("FOURIER_B200_CFG", 0) == 1)
       return FusedImpl<fused::FusedCfg<float, 16, 8, 4, 8, 4, true, 16, 32, 16, 16, 32>>::ops(64, 32);
@@ -254,7 +257,7 @@ cudaError_t Plan<T>::exec_twopass(const C* in, C* out, size_t batch, int code, c
       a.trace = (long long*)trace_.data();
     }
     a.batch = (int)batch; a.ring = ring; a.lag = lag; a.scale = scale; a.do_scale = do_scale ? 1 : 0;
-    const size_t tiles = batch * (f->n1 + f->n2) / (size_t)f->tile_c;
+    const size_t tiles = batch * (f->n2 / (size_t)f->tile_c + f->n1 / 8);
     const int grid = (int)std::min<size_t>((size_t)sm_count_, std::max<size_t>(1, tiles / 2));
     FB_CHECK(f->launch(a, fwd, grid, s));
     launches_ += 1;

@@ -275,7 +275,7 @@ static int check_fused(const char* name, double tol) {
   using T = typename Cfg::T;
   using V = cpx<T>;
   constexpr long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
-  constexpr int C = Cfg::C, GT = Cfg::GT;
+  constexpr int C = Cfg::C, C1 = Cfg::C1, GT = Cfg::GT;
   printf("%s: persistent-kernel arithmetic, N=%ld = %ld x %ld, blocked intermediate%s\n", name, N, N1, N2, Cfg::DIRECT ? ", direct loads" : "");
   report_conflicts<typename Cfg::template Tile1<true>, typename Cfg::Lay1, kMapCF>("pass 1");
   report_conflicts<typename Cfg::template Tile2<true>, typename Cfg::Lay2, fused::FusedMath<Cfg, true>::kMap2>("pass 2");
@@ -307,7 +307,7 @@ static int check_fused(const char* name, double tol) {
       for (int l = 0; l < 32; ++l) {
         const int t = warp * 32 + l;
         const long col = Tile::template col_of<kMapCF>(t), p = Tile::template u_of<kMapCF>(t);
-        const long e = (p >> 3) * (N2 * 8) + (p & 7) * 8 + col;   // output r = 0
+        const long e = (p >> 3) * (N2 * 8) + (col >> 3) * 64 + (p & 7) * 8 + (col & 7);   // output r = 0
         const long line = e * (long)sizeof(V) / 128, tw = TileB::template u_of<M>(t);
         if (std::find(seen_l.begin(), seen_l.end(), line) == seen_l.end()) seen_l.push_back(line);
         if (std::find(seen_t.begin(), seen_t.end(), tw) == seen_t.end()) seen_t.push_back(tw);
@@ -323,10 +323,10 @@ static int check_fused(const char* name, double tol) {
   for (int i = 0; i < (int)twa_pairs.size(); ++i) fused::FusedMath<Cfg, true>::relayout_twa(twa.data(), twa_pairs.data(), i, (int)twa_pairs.size());
   for (int i = 0; i < (int)twa2_pairs.size(); ++i) fused::FusedMath<Cfg, true>::relayout_twa(twa2.data(), twa2_pairs.data(), i, (int)twa2_pairs.size());
   std::vector<V> tbase, tstep;
-  make_factored_twiddles<T>((size_t)N, (size_t)N2, Cfg::RA, Cfg::RB, C, tbase, tstep, true);
+  make_factored_twiddles<T>((size_t)N, (size_t)N2, Cfg::RA, Cfg::RB, C1, tbase, tstep, true);
   int bad = 0;
   for (int fwd = 1; fwd >= 0; --fwd) {
-    std::vector<V> x(N), scratch(N), out(N), staging((size_t)C * std::max(N1, N2)), tab((size_t)Cfg::TAB_ELEMS);
+    std::vector<V> x(N), scratch(N), out(N), staging(std::max((size_t)C1 * N1, (size_t)C * N2)), tab((size_t)Cfg::TAB_ELEMS);
     std::vector<V> exch(Cfg::EX_ELEMS);
     fill<T>(x, 41 + fwd);
     const T scale = (T)0.5;
@@ -337,14 +337,14 @@ static int check_fused(const char* name, double tol) {
       using P = typename Math::template Pass<PASS>;
       std::vector<typename P::Tile> thr(GT);
       // direct mode: the threads read global memory themselves (same pointers as the kernel computes)
-      const V* src = !Cfg::DIRECT ? staging.data() : PASS == 1 ? x.data() + (size_t)tile * C
+      const V* src = !Cfg::DIRECT ? staging.data() : PASS == 1 ? x.data() + (size_t)tile * C1
                                                                 : scratch.data() + (size_t)tile * C * N2;
       for (int t = 0; t < GT; ++t) { P::load(thr[t], t, src); P::stage_a(thr[t], t, PASS == 1 ? twa.data() : twa2.data()); }
       for (int t = 0; t < GT; ++t) P::scatter(thr[t], t, exch.data());
       for (int t = 0; t < GT; ++t) {
         P::gather(thr[t], t, exch.data());
         thr[t].stage_b();
-        if constexpr (PASS == 1) Math::store1(thr[t], t, scratch.data(), tile, tab.data());
+        if constexpr (PASS == 1) Math::store1(thr[t], t, scratch.data(), tile, tab.data(), tab.data() + Cfg::TAB_BASE);
         else Math::store2(thr[t], t, out.data(), tile, true, scale);
       }
     };
@@ -352,7 +352,7 @@ static int check_fused(const char* name, double tol) {
     using Two = std::integral_constant<int, 2>;
     for (int tile = 0; tile < Cfg::T1; ++tile) {        // pass 1: TMA box = rows n1, columns tile*C .. +C
       for (long r = 0; r < N1; ++r)
-        for (int c = 0; c < C; ++c) staging[r * C + c] = x[r * N2 + (long)tile * C + c];
+        for (int c = 0; c < C1; ++c) staging[r * C1 + c] = x[r * N2 + (long)tile * C1 + c];
       for (int i = 0; i < Cfg::TAB_BASE; ++i) tab[i] = tbase[(size_t)tile * Cfg::TAB_BASE + i];
       for (int i = 0; i < Cfg::TAB_STEP; ++i) tab[Cfg::TAB_BASE + i] = tstep[(size_t)tile * Cfg::TAB_STEP + i];
       if (fwd) run_tile(std::true_type{}, One{}, tile); else run_tile(std::false_type{}, One{}, tile);
@@ -561,7 +561,8 @@ int main() {
   bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 8, 2, true>>("fused f32 2^20", 2e-6);
   bad += check_fused<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>("fused f64 2^16", 5e-15);
   bad += check_fused<fused::FusedCfg<double, 8, 8, 8, 4, 8, true>>("fused f64 2^12", 5e-15);
-  // <T, RA, C, G, PAD1, EXB, DIRECT, RB, RA2, RB2, E1, E2>
+  // <T, RA, C, G, PAD1, EXB, DIRECT, RB, RA2, RB2, E1, E2, C1>
+  bad += check_fused<fused::FusedCfg<float, 32, 8, 2, 0, 1, false, 16, 32, 32, 32, 32, 16, true>>("fused f32 2^19", 2e-6);
   bad += check_fused<fused::FusedCfg<float, 16, 8, 6, 8, 6, false, 8, 16, 16, 16, 32>>("fused f32 2^15", 2e-6);
   bad += check_fused<fused::FusedCfg<float, 8, 8, 8, 8, 8, false, 8, 16, 8, 8, 16>>("fused f32 2^13", 2e-6);
   bad += check_fused<fused::FusedCfg<float, 16, 8, 3, 8, 3, false, 16, 32, 16, 16, 32>>("fused f32 2^17", 2e-6);
