@@ -572,13 +572,10 @@ fused_twopass_kernel(const __grid_constant__ CUtensorMap in_map, const FusedArgs
       // ---- stage B and the stores -------------------------------------------------------------------------------
       f.stage_b();
       if constexpr (PASS == 1) {
-        const V* tb = tab_g + (size_t)(k_p1 & 1) * Cfg::TAB_ELEMS;
+        const V* tb = Cfg::TABG ? a.tbase + (size_t)wi.tile * Cfg::TAB_BASE : tab_g + (size_t)(k_p1 & 1) * Cfg::TAB_ELEMS;
+        const V* ts = Cfg::TABG ? a.tstep + (size_t)wi.tile * Cfg::TAB_STEP : tb + Cfg::TAB_BASE;
         ++k_p1;
-        if constexpr (Cfg::TABG)
-          Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, a.tbase + (size_t)wi.tile * Cfg::TAB_BASE,
-                       a.tstep + (size_t)wi.tile * Cfg::TAB_STEP);
-        else
-          Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb, tb + Cfg::TAB_BASE);
+        Math::store1(f, t, a.scratch + (size_t)wi.slot * N, wi.tile, tb, ts);
         // report "stores issued"; the last warp of the group hands the tile to the signaller warp
         __syncwarp();
         if ((t & 31) == 0 && atom_add_acq_rel_cta_shared(&ctl->stored_warps, 1u) == GT / 32 - 1) {

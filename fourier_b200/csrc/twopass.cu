@@ -130,7 +130,7 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
   // Odd powers of two: N1 x 2 N1 with a different register tile per pass, same threads per FFT in both
   // (template arguments: <T, RA, C, G, PAD1, EXB, DIRECT, RB, RA2, RB2, E1, E2>).  Ring = 64 MB / transform size.
   if (n == ((size_t)1 << 19)) {   // 512 (32 x 16) x 1024 (32 x 32), 16-column pass-1 tiles: two 256-thread groups
-    return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 0, 1, false, 16, 32, 32, 32, 32, 16, true>>::ops(16, 8);
+    return FusedImpl<fused::FusedCfg<float, 32, 8, 2, 0, 1, false, 16, 32, 32, 32, 32, 16, true>>::ops(32, 16);   // 39 % (ring 16: 35 %, tile kernels 29 %)
   }
   if (n == ((size_t)1 << 17)) {   // 256 (16 x 16, 16 per thread) x 512 (32 x 16, 32 per thread): three 128-thread groups
     if (env_int("FOURIER_B200_CFG", 0) == 1)
@@ -152,9 +152,12 @@ template <> const FusedOps<float>* fused_lookup<float>(size_t n) {
 }
 template <> const FusedOps<double>* fused_lookup<double>(size_t n) {
   if (n == ((size_t)1 << 16)) {
-    // default: four 128-thread groups loading directly from global memory, one exchange buffer each
-    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
-    return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>::ops(64, 32);
+    // Three 128-thread groups with TMA staging, or four loading directly from global memory.  Short runs are a tie
+    // (62.5 % / 59.9 % at batch 2048, 57.9 % / 58.8 % at 16384); at the BASELINE batch of 65536, where the run is
+    // power-capped at ~1760 MHz, staging wins twice out of two A/B pairs: 56.5 / 57.4 % against 54.3 / 54.4 %
+    // (profiles/r02_c3_staged_vs_direct.txt).
+    if (env_int("FOURIER_B200_CFG", 0) == 1) return FusedImpl<fused::FusedCfg<double, 16, 8, 4, 4, 4, true>>::ops(64, 32);
+    return FusedImpl<fused::FusedCfg<double, 16, 8, 3, 4, 3>>::ops(64, 32);
   }
   if (n == ((size_t)1 << 14)) {
     // 128 x 128 with 16 x 8 register tiles: four 64-thread groups with TMA staging, or eight loading directly
