@@ -1,30 +1,16 @@
 #!/bin/bash
-# First GPU call of the next round: run the emulator-only variants on hardware and measure them against the default.
-#   gpurun --timeout 1500 -- 'bash tools/measure_variants.sh'            (one B200, ~6 min)
-# Writes gpurun_out/variants_{tests,bench}.log.  FOURIER_B200_CFG: 0 default, 5 blocked intermediate, 6 blocked +
-# direct loads (no staging), 7 blocked + direct loads in pass 2 only.
+# Load-strategy A/B of the persistent two-pass kernel on one B200 (FOURIER_B200_CFG: 0 = the size's default,
+# 1 = the other strategy: TMA staging <-> direct global loads; FOURIER_B200_FUSED=0 = two-launch tile kernels):
+#   gpurun --timeout 1500 -- 'bash tools/measure_variants.sh'
+# Round 2's first call ran the round-1 variants 0/5/6/7 with this script (profiles/r02_persistent_kernel_variants.txt);
+# the losers were deleted, what remains is the per-size choice between the two load strategies.
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
-FOURIER_B200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_distributed.py -q \
-  -k "experimental or persistent_variant" > gpurun_out/variants_tests.log 2>&1
-tail -5 gpurun_out/variants_tests.log
+export PYTHONPATH=.
 : > gpurun_out/variants_bench.log
-for cfg in 0 5 7 6; do
-  echo "== c2 cfg $cfg" >> gpurun_out/variants_bench.log
-  FOURIER_B200_CFG=$cfg timeout 300 python bench.py --batch 1024 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 >> gpurun_out/variants_bench.log
-  echo "== c3 cfg $cfg" >> gpurun_out/variants_bench.log
-  FOURIER_B200_CFG=$cfg timeout 300 python bench.py --workload c3 --batch 16384 --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 >> gpurun_out/variants_bench.log
+for real_sizes in "f32 2^13 2^14 2^15 2^16 2^17 2^18 2^19 2^20" "f64 2^12 2^13 2^14 2^16"; do
+  set -- $real_sizes; real=$1; shift
+  for cfg in 0 1; do FOURIER_B200_CFG=$cfg python tools/size_table.py $real "$@" >> gpurun_out/variants_bench.log 2>&1; done
+  FOURIER_B200_FUSED=0 python tools/size_table.py $real "$@" >> gpurun_out/variants_bench.log 2>&1
 done
-python - <<'PY'
-import json
-for l in open('gpurun_out/variants_bench.log'):
-    l = l.strip()
-    if l.startswith('=='):
-        print(l, end='   ')
-    elif l.startswith('{'):
-        d = json.loads(l)
-        print('%.3e samples/s  %.1f %% of measured HBM peak  %.3f ms/step  verify %s' % (
-            d['value'], 100 * d['roofline']['frac'], d['ms_per_step'], d.get('verify')))
-    elif l:
-        print(l[:160])
-PY
+cat gpurun_out/variants_bench.log
