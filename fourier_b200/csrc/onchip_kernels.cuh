@@ -200,6 +200,35 @@ template <class Cfg> struct BluesteinBody {
       });
     });
   }
+  // ---- paired mode: one warp per half-transform.  The odd-half warp hands o' = O' * w_M^n to the even-half warp through
+  // its own (now idle) exchange region, register idx of lane l at xfer[idx * 32 + l]; no stash at all.
+  static FB_HD void handoff_store(const Tile& f, int t, V* xfer, const V* wm) {
+    static_assert(TP == 32, "paired mode: one warp per FFT");
+    const int u = Tile::template u_of<true>(t);
+    static_for<0, Tile::NB>([&](auto Cc) FB_LAMBDA {
+      constexpr int c = decltype(Cc)::value;
+      static_for<0, RB>([&](auto Rr) FB_LAMBDA {
+        constexpr int r = decltype(Rr)::value;
+        constexpr int idx = c * RB + bitrev(r, ilog2(RB));
+        xfer[idx * 32 + u] = cmul(f.v[idx], wm[pos_out(u, c, r)]);
+      });
+    });
+  }
+  static FB_HD void combine_store_paired(const Tile& f, const Args& a, long b, int t, const V* xfer, const V* chirp) {
+    const int u = Tile::template u_of<true>(t);
+    V* p = a.out + b * a.n;
+    static_for<0, Tile::NB>([&](auto Cc) FB_LAMBDA {
+      constexpr int c = decltype(Cc)::value;
+      static_for<0, RB>([&](auto Rr) FB_LAMBDA {
+        constexpr int r = decltype(Rr)::value;
+        const int n = pos_out(u, c, r);
+        if (n < a.n) {
+          constexpr int idx = c * RB + bitrev(r, ilog2(RB));
+          p[n] = cscale(cmul_conja(cadd(f.v[idx], xfer[idx * 32 + u]), chirp[n]), a.scale);
+        }
+      });
+    });
+  }
   static FB_HD void combine_store(const V* stash, const Tile& f, const Args& a, long b, int t, const V* chirp,
                                   const V* wm) {
     const int u = Tile::template u_of<true>(t);
@@ -276,6 +305,76 @@ bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
     }
     __syncwarp();
   }
+}
+
+// Paired variant for L = 1024 (one warp = one 1024-point FFT): warps 2p and 2p+1 compute the even and the odd half of
+// the same transform IN PARALLEL and meet once, through shared memory, at the combine.  Against the kernel above: no
+// thread-local stash (its 8 KB per transform went through L1 to DRAM: 17.6 instead of 16 B/sample, profiles/
+// r02_c4_bluestein_ncu_summary.txt), 64 data registers per thread instead of 128, so 20 instead of 16 resident warps.
+// One named barrier per pair, used alternately in both directions (odd arrives / even waits: o' is ready; even
+// arrives / odd waits: the region may be overwritten).
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <class Cfg, int MINB>
+__global__ void __launch_bounds__(Cfg::THREADS, MINB)
+bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
+  using Body = BluesteinBody<Cfg>;
+  using V = typename Cfg::Tile::V;
+  using T = decltype(V::x);
+  constexpr int L = Cfg::L;
+  static_assert(Cfg::TP == 32 && Cfg::THREADS % 64 == 0 && Cfg::THREADS / 64 <= 15, "one warp per FFT, warps in pairs");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  V* exch = reinterpret_cast<V*>(smem_raw);
+  TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(smem_raw + Cfg::EX_BYTES);
+  V* tabs = reinterpret_cast<V*>(smem_raw + Cfg::EX_BYTES + Cfg::TWA_BYTES);
+  V* chirp = tabs; V* wm = tabs + L; V* wce = tabs + 2 * L; V* wco = tabs + 3 * L;
+  for (int i = threadIdx.x; i < (Cfg::Tile::RA / 2) * Cfg::Tile::RB; i += Cfg::THREADS) twa[i] = a.twa[i];
+  for (int i = threadIdx.x; i < L; i += Cfg::THREADS) {
+    chirp[i] = a.chirp[i]; wm[i] = a.wm[i]; wce[i] = a.wce[i]; wco[i] = a.wco[i];
+  }
+  __syncthreads();
+  const int t = threadIdx.x, warp = t >> 5, pair = warp >> 1;
+  const bool odd = (warp & 1) != 0;
+  const int bar = 1 + pair;
+  constexpr int kPairs = Cfg::THREADS / 64;
+  V* xfer = exch + (warp | 1) * Cfg::Lay::SC;   // the odd warp's exchange region, idle once its second FFT is done
+  const long groups = (a.batch + kPairs - 1) / kPairs;
+  typename Cfg::Tile f;
+  bool first = true;
+  for (long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const long b_real = grp * kPairs + pair;
+    const long b = b_real < a.batch ? b_real : a.batch - 1;
+    if (odd) {
+      if (!first) pair_sync(bar);            // the even warp has read the previous o': the region is ours again
+      Body::template load_half<true>(f, a, b, t, exch, twa, chirp, wm);
+      __syncwarp();
+      Body::middle(f, t, exch, wco);
+      __syncwarp();
+      Body::second_fft_start(f, t, exch, twa);
+      __syncwarp();
+      Body::second_fft_finish(f, t, exch);
+      __syncwarp();                          // every lane has gathered before the region is reused for the hand-off
+      Body::handoff_store(f, t, xfer, wm);
+      __threadfence_block();
+      pair_arrive(bar);
+    } else {
+      Body::template load_half<false>(f, a, b, t, exch, twa, chirp, wm);
+      __syncwarp();
+      Body::middle(f, t, exch, wce);
+      __syncwarp();
+      Body::second_fft_start(f, t, exch, twa);
+      __syncwarp();
+      Body::second_fft_finish(f, t, exch);
+      pair_sync(bar);                        // o' of the odd half has landed
+      if (b_real < a.batch) Body::combine_store_paired(f, a, b, t, xfer, chirp);
+      __threadfence_block();
+      pair_arrive(bar);
+      __syncwarp();
+    }
+    first = false;
+  }
+  if (odd && !first) pair_sync(bar);         // consume the even warp's last arrival
 }
 
 }  // namespace onchip
