@@ -129,6 +129,11 @@ template <class Cfg> struct BluesteinBody {
   template <bool ODD>
   static FB_HD void load_half(Tile& f, const Args& a, long b, int t, V* smem, const TwPair<T>* twa,
                               const V* chirp, const V* wm) {
+    load_half_rt(f, a, b, t, smem, twa, chirp, wm, ODD);
+  }
+  // same with the half chosen at run time (paired kernel: one copy of the code serves both warps of a pair)
+  static FB_HD void load_half_rt(Tile& f, const Args& a, long b, int t, V* smem, const TwPair<T>* twa,
+                                 const V* chirp, const V* wm, bool ODD) {
     const int u = Tile::template u_of<true>(t);
     const V* p = a.in + b * a.n;
     static_for<0, Tile::NA>([&](auto Q) FB_LAMBDA {
@@ -345,27 +350,20 @@ bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
   for (long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const long b_real = grp * kPairs + pair;
     const long b = b_real < a.batch ? b_real : a.batch - 1;
+    if (odd && !first) pair_sync(bar);       // the even warp has read the previous o': the region is ours again
+    Body::load_half_rt(f, a, b, t, exch, twa, chirp, wm, odd);
+    __syncwarp();
+    Body::middle(f, t, exch, odd ? wco : wce);
+    __syncwarp();
+    Body::second_fft_start(f, t, exch, twa);
+    __syncwarp();
+    Body::second_fft_finish(f, t, exch);
     if (odd) {
-      if (!first) pair_sync(bar);            // the even warp has read the previous o': the region is ours again
-      Body::template load_half<true>(f, a, b, t, exch, twa, chirp, wm);
-      __syncwarp();
-      Body::middle(f, t, exch, wco);
-      __syncwarp();
-      Body::second_fft_start(f, t, exch, twa);
-      __syncwarp();
-      Body::second_fft_finish(f, t, exch);
       __syncwarp();                          // every lane has gathered before the region is reused for the hand-off
       Body::handoff_store(f, t, xfer, wm);
       __threadfence_block();
       pair_arrive(bar);
     } else {
-      Body::template load_half<false>(f, a, b, t, exch, twa, chirp, wm);
-      __syncwarp();
-      Body::middle(f, t, exch, wce);
-      __syncwarp();
-      Body::second_fft_start(f, t, exch, twa);
-      __syncwarp();
-      Body::second_fft_finish(f, t, exch);
       pair_sync(bar);                        // o' of the odd half has landed
       if (b_real < a.batch) Body::combine_store_paired(f, a, b, t, xfer, chirp);
       __threadfence_block();
