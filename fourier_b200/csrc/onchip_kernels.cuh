@@ -153,6 +153,22 @@ template <class Cfg> struct BluesteinBody {
     f.template scatter<true, typename Cfg::Lay>(t, smem);
   }
 
+  // paired kernel: x * tab, tab = chirp (even half) or the folded chirp * w_M^n (odd half): one multiply, one table
+  static FB_HD void load_times(Tile& f, const Args& a, long b, int t, V* smem, const TwPair<T>* twa, const V* tab) {
+    const int u = Tile::template u_of<true>(t);
+    const V* p = a.in + b * a.n;
+    static_for<0, Tile::NA>([&](auto Q) FB_LAMBDA {
+      constexpr int q = decltype(Q)::value;
+      static_for<0, RA>([&](auto I) FB_LAMBDA {
+        constexpr int i = decltype(I)::value;
+        const int n = pos_in(u, q, i);
+        f.v[q * RA + i] = n < a.n ? cmul(p[n], tab[n]) : mk<T>((T)0, (T)0);
+      });
+    });
+    f.template stage_a<true>(t, twa);
+    f.template scatter<true, typename Cfg::Lay>(t, smem);
+  }
+
   // finish the forward FFT and multiply by conj(W) in the conjugate domain.  The outputs sit at
   // bit-reversed register positions while the next stage A wants natural order: for the square tiles
   // used here (RA == RB, one butterfly per thread and stage) output r of this FFT is input i = r of
@@ -333,10 +349,12 @@ bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
   V* exch = reinterpret_cast<V*>(smem_raw);
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(smem_raw + Cfg::EX_BYTES);
   V* tabs = reinterpret_cast<V*>(smem_raw + Cfg::EX_BYTES + Cfg::TWA_BYTES);
-  V* chirp = tabs; V* wm = tabs + L; V* wce = tabs + 2 * L; V* wco = tabs + 3 * L;
+  V* chirp = tabs; V* wm = tabs + L; V* wce = tabs + 2 * L; V* wco = tabs + 3 * L; V* cw = tabs + 4 * L;
   for (int i = threadIdx.x; i < (Cfg::Tile::RA / 2) * Cfg::Tile::RB; i += Cfg::THREADS) twa[i] = a.twa[i];
   for (int i = threadIdx.x; i < L; i += Cfg::THREADS) {
-    chirp[i] = a.chirp[i]; wm[i] = a.wm[i]; wce[i] = a.wce[i]; wco[i] = a.wco[i];
+    const V c = a.chirp[i], w = a.wm[i];
+    chirp[i] = c; wm[i] = w; wce[i] = a.wce[i]; wco[i] = a.wco[i];
+    cw[i] = cmul(c, w);                      // the odd half loads x * chirp * w_M^n with one multiply
   }
   __syncthreads();
   const int t = threadIdx.x, warp = t >> 5, pair = warp >> 1;
@@ -351,7 +369,7 @@ bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
     const long b_real = grp * kPairs + pair;
     const long b = b_real < a.batch ? b_real : a.batch - 1;
     if (odd && !first) pair_sync(bar);       // the even warp has read the previous o': the region is ours again
-    Body::load_half_rt(f, a, b, t, exch, twa, chirp, wm, odd);
+    Body::load_times(f, a, b, t, exch, twa, odd ? cw : chirp);
     __syncwarp();
     Body::middle(f, t, exch, odd ? wco : wce);
     __syncwarp();

@@ -242,8 +242,9 @@ static int check_bluestein(const char* name, long n, double tol) {
         auto pbc = [&](int t) { long b = pb(t); return b < batch ? b : batch - 1; };
         for (int odd = 1; odd >= 0; --odd) {
           auto half = [&](auto fn) { for (int t = 0; t < Cfg::THREADS; ++t) if ((((t >> 5) & 1) != 0) == (odd != 0)) fn(t); };
-          half([&](int t) { if (odd) Body::template load_half<true>(thr[t], a, pbc(t), t, exch.data(), twa.data(), chirp.data(), wm.data());
-                            else Body::template load_half<false>(thr[t], a, pbc(t), t, exch.data(), twa.data(), chirp.data(), wm.data()); });
+          std::vector<V> cw(L);
+          for (long i = 0; i < L; ++i) cw[i] = cmul(chirp[i], wm[i]);
+          half([&](int t) { Body::load_times(thr[t], a, pbc(t), t, exch.data(), twa.data(), odd ? cw.data() : chirp.data()); });
           half([&](int t) { Body::middle(thr[t], t, exch.data(), odd ? wco.data() : wce.data()); });
           half([&](int t) { Body::second_fft_start(thr[t], t, exch.data(), twa.data()); });
           half([&](int t) { Body::second_fft_finish(thr[t], t, exch.data()); });
