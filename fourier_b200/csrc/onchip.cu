@@ -94,7 +94,7 @@ struct OnChipImpl {
 // plugged into the ops of the 1024-point size class.
 template <typename T, int WARPS> struct PairedBluestein {
   using BCfg = OnChipCfg<T, 32, 32, 32, WARPS, true>;
-  static constexpr size_t smem = BCfg::EX_BYTES + BCfg::TWA_BYTES + sizeof(cpx<T>) * 5 * (size_t)BCfg::L;   // + chirp * w_M
+  static constexpr size_t smem = BCfg::EX_BYTES + BCfg::TWA_BYTES + sizeof(cpx<T>) * 5 * (size_t)BCfg::L + 8 * WARPS;   // + chirp * w_M, mbarriers
   static_assert(smem <= 227 * 1024, "paired Bluestein kernel: shared memory");
   static cudaError_t prepare() {
     return cudaFuncSetAttribute(onchip::bluestein_paired_kernel<BCfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -16,6 +16,8 @@
 // multiplies, so only the forward tile is instantiated.
 #pragma once
 
+#include <cstdint>
+
 #include "tilefft.cuh"
 
 namespace fb200 {
@@ -332,10 +334,23 @@ bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
 // the same transform IN PARALLEL and meet once, through shared memory, at the combine.  Against the kernel above: no
 // thread-local stash (its 8 KB per transform went through L1 to DRAM: 17.6 instead of 16 B/sample, profiles/
 // r02_c4_bluestein_ncu_summary.txt), 64 data registers per thread instead of 128, so 20 instead of 16 resident warps.
-// One named barrier per pair, used alternately in both directions (odd arrives / even waits: o' is ready; even
-// arrives / odd waits: the region may be overwritten).
-__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+// Two mbarriers per pair (ready: o' has been written; free: it has been read).  A first version used ONE named barrier
+// alternately in both directions and hung on the GPU: the odd warp's bar.arrive plus its own later bar.sync add up to
+// the expected 64 arrivals without the even warp -- and there are not enough named barriers for two per pair.
+__device__ __forceinline__ void pb_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void pb_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void pb_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (unsigned spins = 0; !ok; ++spins) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    if (spins > (1u << 22)) __trap();   // a protocol bug must abort the kernel, never hang the GPU
+  }
+}
 
 template <class Cfg, int MINB>
 __global__ void __launch_bounds__(Cfg::THREADS, MINB)
@@ -344,12 +359,15 @@ bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
   using V = typename Cfg::Tile::V;
   using T = decltype(V::x);
   constexpr int L = Cfg::L;
-  static_assert(Cfg::TP == 32 && Cfg::THREADS % 64 == 0 && Cfg::THREADS / 64 <= 15, "one warp per FFT, warps in pairs");
+  static_assert(Cfg::TP == 32 && Cfg::THREADS % 64 == 0, "one warp per FFT, warps in pairs");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   V* exch = reinterpret_cast<V*>(smem_raw);
   TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(smem_raw + Cfg::EX_BYTES);
   V* tabs = reinterpret_cast<V*>(smem_raw + Cfg::EX_BYTES + Cfg::TWA_BYTES);
   V* chirp = tabs; V* wm = tabs + L; V* wce = tabs + 2 * L; V* wco = tabs + 3 * L; V* cw = tabs + 4 * L;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tabs + 5 * L);   // [pair][ready, free]
+  if (threadIdx.x < Cfg::THREADS / 32) pb_init(&bars[threadIdx.x], 32);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int i = threadIdx.x; i < (Cfg::Tile::RA / 2) * Cfg::Tile::RB; i += Cfg::THREADS) twa[i] = a.twa[i];
   for (int i = threadIdx.x; i < L; i += Cfg::THREADS) {
     const V c = a.chirp[i], w = a.wm[i];
@@ -359,16 +377,17 @@ bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
   __syncthreads();
   const int t = threadIdx.x, warp = t >> 5, pair = warp >> 1;
   const bool odd = (warp & 1) != 0;
-  const int bar = 1 + pair;
+  uint64_t* ready = &bars[2 * pair];
+  uint64_t* freed = &bars[2 * pair + 1];
   constexpr int kPairs = Cfg::THREADS / 64;
   V* xfer = exch + (warp | 1) * Cfg::Lay::SC;   // the odd warp's exchange region, idle once its second FFT is done
   const long groups = (a.batch + kPairs - 1) / kPairs;
   typename Cfg::Tile f;
-  bool first = true;
-  for (long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+  uint32_t it = 0;
+  for (long grp = blockIdx.x; grp < groups; grp += gridDim.x, ++it) {
     const long b_real = grp * kPairs + pair;
     const long b = b_real < a.batch ? b_real : a.batch - 1;
-    if (odd && !first) pair_sync(bar);       // the even warp has read the previous o': the region is ours again
+    if (odd && it > 0) pb_wait(freed, (it - 1) & 1);   // the even warp has read the previous o': the region is ours again
     Body::load_times(f, a, b, t, exch, twa, odd ? cw : chirp);
     __syncwarp();
     Body::middle(f, t, exch, odd ? wco : wce);
@@ -379,18 +398,13 @@ bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
     if (odd) {
       __syncwarp();                          // every lane has gathered before the region is reused for the hand-off
       Body::handoff_store(f, t, xfer, wm);
-      __threadfence_block();
-      pair_arrive(bar);
+      pb_arrive(ready);                      // release: the stores above are visible to whoever observes the phase
     } else {
-      pair_sync(bar);                        // o' of the odd half has landed
+      pb_wait(ready, it & 1);                // o' of the odd half has landed
       if (b_real < a.batch) Body::combine_store_paired(f, a, b, t, xfer, chirp);
-      __threadfence_block();
-      pair_arrive(bar);
-      __syncwarp();
+      pb_arrive(freed);
     }
-    first = false;
   }
-  if (odd && !first) pair_sync(bar);         // consume the even warp's last arrival
 }
 
 }  // namespace onchip
