@@ -90,39 +90,6 @@ struct OnChipImpl {
   }
 };
 
-// The paired Bluestein kernel (two warps per transform, onchip_kernels.cuh) for L = 1024 with WARPS warps per CTA,
-// plugged into the ops of the 1024-point size class.
-template <typename T, int WARPS> struct PairedBluestein {
-  using BCfg = OnChipCfg<T, 32, 32, 32, WARPS, true>;
-  static constexpr size_t smem = BCfg::EX_BYTES + BCfg::TWA_BYTES + sizeof(cpx<T>) * 5 * (size_t)BCfg::L + 8 * WARPS;   // + chirp * w_M, mbarriers
-  static_assert(smem <= 227 * 1024, "paired Bluestein kernel: shared memory");
-  static cudaError_t prepare() {
-    return cudaFuncSetAttribute(onchip::bluestein_paired_kernel<BCfg, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem);
-  }
-  static cudaError_t launch(const cpx<T>* in, cpx<T>* out, const void* twa, const cpx<T>* chirp, const cpx<T>* wm,
-                            const cpx<T>* wce, const cpx<T>* wco, size_t n, size_t batch, T scale, int sms,
-                            cudaStream_t s) {
-    constexpr size_t pairs = WARPS / 2;
-    const size_t groups = (batch + pairs - 1) / pairs;
-    const unsigned grid = (unsigned)std::min<size_t>(groups, (size_t)sms);
-    typename onchip::BluesteinBody<BCfg>::Args a = {in, out, (const TwPair<T>*)twa, chirp, wm, wce, wco,
-                                                    (long)n, (long)batch, scale};
-    onchip::bluestein_paired_kernel<BCfg, 1><<<grid, BCfg::THREADS, smem, s>>>(a);
-    return cudaGetLastError();
-  }
-  // the 1024-point ops with the Bluestein entry replaced
-  static const OnChipOps<T>* ops(const OnChipOps<T>* base) {
-    static OnChipOps<T> o;
-    static cudaError_t (*base_prepare)() = nullptr;
-    o = *base;
-    base_prepare = base->prepare;
-    o.prepare = [] { cudaError_t e = base_prepare(); return e != cudaSuccess ? e : prepare(); };
-    o.bluestein = &launch;
-    return &o;
-  }
-};
-
 // size classes: L -> (RA, RB, E, warps per CTA, CTAs per SM, warps per CTA of the Bluestein kernel)
 template <typename T> const OnChipOps<T>* onchip_lookup(size_t l);
 template <> const OnChipOps<float>* onchip_lookup<float>(size_t l) {
@@ -137,16 +104,6 @@ template <> const OnChipOps<float>* onchip_lookup<float>(size_t l) {
       // (11 warps per SM, 1.01e11).
       if (const char* e = std::getenv("FOURIER_B200_BLUESTEIN_LOCAL"); e && atoi(e) == 0)
         return OnChipImpl<float, 32, 32, 32, 8, 2, 11>::ops();
-      // FOURIER_B200_BLUESTEIN_PAIRED=w: two warps per transform (even / odd half in parallel), w warps per CTA
-      if (const char* e = std::getenv("FOURIER_B200_BLUESTEIN_PAIRED")) {
-        const OnChipOps<float>* base = OnChipImpl<float, 32, 32, 32, 8, 2, 16, true>::ops();
-        switch (atoi(e)) {
-          case 16: return PairedBluestein<float, 16>::ops(base);
-          case 20: return PairedBluestein<float, 20>::ops(base);
-          case 18: return PairedBluestein<float, 18>::ops(base);
-          default: break;
-        }
-      }
       return OnChipImpl<float, 32, 32, 32, 8, 2, 16, true>::ops();
     default: return nullptr;
   }

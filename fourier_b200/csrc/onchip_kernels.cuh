@@ -16,8 +16,6 @@
 // multiplies, so only the forward tile is instantiated.
 #pragma once
 
-#include <cstdint>
-
 #include "tilefft.cuh"
 
 namespace fb200 {
@@ -131,11 +129,6 @@ template <class Cfg> struct BluesteinBody {
   template <bool ODD>
   static FB_HD void load_half(Tile& f, const Args& a, long b, int t, V* smem, const TwPair<T>* twa,
                               const V* chirp, const V* wm) {
-    load_half_rt(f, a, b, t, smem, twa, chirp, wm, ODD);
-  }
-  // same with the half chosen at run time (paired kernel: one copy of the code serves both warps of a pair)
-  static FB_HD void load_half_rt(Tile& f, const Args& a, long b, int t, V* smem, const TwPair<T>* twa,
-                                 const V* chirp, const V* wm, bool ODD) {
     const int u = Tile::template u_of<true>(t);
     const V* p = a.in + b * a.n;
     static_for<0, Tile::NA>([&](auto Q) FB_LAMBDA {
@@ -149,22 +142,6 @@ template <class Cfg> struct BluesteinBody {
           if (ODD) v = cmul(v, wm[n]);
         }
         f.v[q * RA + i] = v;
-      });
-    });
-    f.template stage_a<true>(t, twa);
-    f.template scatter<true, typename Cfg::Lay>(t, smem);
-  }
-
-  // paired kernel: x * tab, tab = chirp (even half) or the folded chirp * w_M^n (odd half): one multiply, one table
-  static FB_HD void load_times(Tile& f, const Args& a, long b, int t, V* smem, const TwPair<T>* twa, const V* tab) {
-    const int u = Tile::template u_of<true>(t);
-    const V* p = a.in + b * a.n;
-    static_for<0, Tile::NA>([&](auto Q) FB_LAMBDA {
-      constexpr int q = decltype(Q)::value;
-      static_for<0, RA>([&](auto I) FB_LAMBDA {
-        constexpr int i = decltype(I)::value;
-        const int n = pos_in(u, q, i);
-        f.v[q * RA + i] = n < a.n ? cmul(p[n], tab[n]) : mk<T>((T)0, (T)0);
       });
     });
     f.template stage_a<true>(t, twa);
@@ -219,35 +196,6 @@ template <class Cfg> struct BluesteinBody {
           constexpr int idx = c * RB + bitrev(r, ilog2(RB));
           const V o = cmul(f.v[idx], wm[n]);
           p[n] = cscale(cmul_conja(cadd(keep[idx], o), chirp[n]), a.scale);
-        }
-      });
-    });
-  }
-  // ---- paired mode: one warp per half-transform.  The odd-half warp hands o' = O' * w_M^n to the even-half warp through
-  // its own (now idle) exchange region, register idx of lane l at xfer[idx * 32 + l]; no stash at all.
-  static FB_HD void handoff_store(const Tile& f, int t, V* xfer, const V* wm) {
-    static_assert(TP == 32, "paired mode: one warp per FFT");
-    const int u = Tile::template u_of<true>(t);
-    static_for<0, Tile::NB>([&](auto Cc) FB_LAMBDA {
-      constexpr int c = decltype(Cc)::value;
-      static_for<0, RB>([&](auto Rr) FB_LAMBDA {
-        constexpr int r = decltype(Rr)::value;
-        constexpr int idx = c * RB + bitrev(r, ilog2(RB));
-        xfer[idx * 32 + u] = cmul(f.v[idx], wm[pos_out(u, c, r)]);
-      });
-    });
-  }
-  static FB_HD void combine_store_paired(const Tile& f, const Args& a, long b, int t, const V* xfer, const V* chirp) {
-    const int u = Tile::template u_of<true>(t);
-    V* p = a.out + b * a.n;
-    static_for<0, Tile::NB>([&](auto Cc) FB_LAMBDA {
-      constexpr int c = decltype(Cc)::value;
-      static_for<0, RB>([&](auto Rr) FB_LAMBDA {
-        constexpr int r = decltype(Rr)::value;
-        const int n = pos_out(u, c, r);
-        if (n < a.n) {
-          constexpr int idx = c * RB + bitrev(r, ilog2(RB));
-          p[n] = cscale(cmul_conja(cadd(f.v[idx], xfer[idx * 32 + u]), chirp[n]), a.scale);
         }
       });
     });
@@ -327,83 +275,6 @@ bluestein_fused_kernel(const typename BluesteinBody<Cfg>::Args a) {
       else Body::combine_store(stash_smem, f, a, b, t, chirp, wm);
     }
     __syncwarp();
-  }
-}
-
-// Paired variant for L = 1024 (one warp = one 1024-point FFT): warps 2p and 2p+1 compute the even and the odd half of
-// the same transform IN PARALLEL and meet once, through shared memory, at the combine.  Against the kernel above: no
-// thread-local stash (its 8 KB per transform went through L1 to DRAM: 17.6 instead of 16 B/sample, profiles/
-// r02_c4_bluestein_ncu_summary.txt), 64 data registers per thread instead of 128, so 20 instead of 16 resident warps.
-// Two mbarriers per pair (ready: o' has been written; free: it has been read).  A first version used ONE named barrier
-// alternately in both directions and hung on the GPU: the odd warp's bar.arrive plus its own later bar.sync add up to
-// the expected 64 arrivals without the even warp -- and there are not enough named barriers for two per pair.
-__device__ __forceinline__ void pb_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void pb_arrive(uint64_t* bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
-}
-__device__ __forceinline__ void pb_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (unsigned spins = 0; !ok; ++spins) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
-    if (spins > (1u << 22)) __trap();   // a protocol bug must abort the kernel, never hang the GPU
-  }
-}
-
-template <class Cfg, int MINB>
-__global__ void __launch_bounds__(Cfg::THREADS, MINB)
-bluestein_paired_kernel(const typename BluesteinBody<Cfg>::Args a) {
-  using Body = BluesteinBody<Cfg>;
-  using V = typename Cfg::Tile::V;
-  using T = decltype(V::x);
-  constexpr int L = Cfg::L;
-  static_assert(Cfg::TP == 32 && Cfg::THREADS % 64 == 0, "one warp per FFT, warps in pairs");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  V* exch = reinterpret_cast<V*>(smem_raw);
-  TwPair<T>* twa = reinterpret_cast<TwPair<T>*>(smem_raw + Cfg::EX_BYTES);
-  V* tabs = reinterpret_cast<V*>(smem_raw + Cfg::EX_BYTES + Cfg::TWA_BYTES);
-  V* chirp = tabs; V* wm = tabs + L; V* wce = tabs + 2 * L; V* wco = tabs + 3 * L; V* cw = tabs + 4 * L;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tabs + 5 * L);   // [pair][ready, free]
-  if (threadIdx.x < Cfg::THREADS / 32) pb_init(&bars[threadIdx.x], 32);
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  for (int i = threadIdx.x; i < (Cfg::Tile::RA / 2) * Cfg::Tile::RB; i += Cfg::THREADS) twa[i] = a.twa[i];
-  for (int i = threadIdx.x; i < L; i += Cfg::THREADS) {
-    const V c = a.chirp[i], w = a.wm[i];
-    chirp[i] = c; wm[i] = w; wce[i] = a.wce[i]; wco[i] = a.wco[i];
-    cw[i] = cmul(c, w);                      // the odd half loads x * chirp * w_M^n with one multiply
-  }
-  __syncthreads();
-  const int t = threadIdx.x, warp = t >> 5, pair = warp >> 1;
-  const bool odd = (warp & 1) != 0;
-  uint64_t* ready = &bars[2 * pair];
-  uint64_t* freed = &bars[2 * pair + 1];
-  constexpr int kPairs = Cfg::THREADS / 64;
-  V* xfer = exch + (warp | 1) * Cfg::Lay::SC;   // the odd warp's exchange region, idle once its second FFT is done
-  const long groups = (a.batch + kPairs - 1) / kPairs;
-  typename Cfg::Tile f;
-  uint32_t it = 0;
-  for (long grp = blockIdx.x; grp < groups; grp += gridDim.x, ++it) {
-    const long b_real = grp * kPairs + pair;
-    const long b = b_real < a.batch ? b_real : a.batch - 1;
-    if (odd && it > 0) pb_wait(freed, (it - 1) & 1);   // the even warp has read the previous o': the region is ours again
-    Body::load_times(f, a, b, t, exch, twa, odd ? cw : chirp);
-    __syncwarp();
-    Body::middle(f, t, exch, odd ? wco : wce);
-    __syncwarp();
-    Body::second_fft_start(f, t, exch, twa);
-    __syncwarp();
-    Body::second_fft_finish(f, t, exch);
-    if (odd) {
-      __syncwarp();                          // every lane has gathered before the region is reused for the hand-off
-      Body::handoff_store(f, t, xfer, wm);
-      pb_arrive(ready);                      // release: the stores above are visible to whoever observes the phase
-    } else {
-      pb_wait(ready, it & 1);                // o' of the odd half has landed
-      if (b_real < a.batch) Body::combine_store_paired(f, a, b, t, xfer, chirp);
-      pb_arrive(freed);
-    }
   }
 }
 

@@ -194,7 +194,7 @@ static int check_onchip(const char* name, double tol) {
   return bad;
 }
 
-template <typename T, int R, int WARPS, bool PAIRED = false>
+template <typename T, int R, int WARPS>
 static int check_bluestein(const char* name, long n, double tol) {
   using Cfg = onchip::OnChipCfg<T, R, R, R, WARPS, true>;
   using Body = onchip::BluesteinBody<Cfg>;
@@ -229,29 +229,11 @@ static int check_bluestein(const char* name, long n, double tol) {
     std::vector<V> exch(Cfg::Tile::template smem_elems<typename Cfg::Lay>());
     std::vector<V> stash((size_t)R * Cfg::THREADS);
     std::vector<typename Cfg::Tile> thr(Cfg::THREADS);
-    const long groups = PAIRED ? (batch + Cfg::THREADS / 64 - 1) / (Cfg::THREADS / 64) : (batch + Cfg::C - 1) / Cfg::C;
+    const long groups = (batch + Cfg::C - 1) / Cfg::C;
     auto all = [&](auto fn) { for (int t = 0; t < Cfg::THREADS; ++t) fn(t); };
     for (long g = 0; g < groups; ++g) {
       auto bidx = [&](int t) { long b = g * Cfg::C + Cfg::Tile::template col_of<true>(t); return b; };
       auto bcl = [&](int t) { long b = bidx(t); return b < batch ? b : batch - 1; };
-      if constexpr (PAIRED) {
-        // paired kernel: warp 2p = even half, warp 2p + 1 = odd half of transform g * pairs + p; the odd warps run
-        // through their hand-off first (the even warps wait for it at the pair barrier)
-        constexpr int pairs = Cfg::THREADS / 64;
-        auto pb = [&](int t) { long b = g * pairs + (t >> 6); return b; };
-        auto pbc = [&](int t) { long b = pb(t); return b < batch ? b : batch - 1; };
-        for (int odd = 1; odd >= 0; --odd) {
-          auto half = [&](auto fn) { for (int t = 0; t < Cfg::THREADS; ++t) if ((((t >> 5) & 1) != 0) == (odd != 0)) fn(t); };
-          std::vector<V> cw(L);
-          for (long i = 0; i < L; ++i) cw[i] = cmul(chirp[i], wm[i]);
-          half([&](int t) { Body::load_times(thr[t], a, pbc(t), t, exch.data(), twa.data(), odd ? cw.data() : chirp.data()); });
-          half([&](int t) { Body::middle(thr[t], t, exch.data(), odd ? wco.data() : wce.data()); });
-          half([&](int t) { Body::second_fft_start(thr[t], t, exch.data(), twa.data()); });
-          half([&](int t) { Body::second_fft_finish(thr[t], t, exch.data()); });
-          if (odd) half([&](int t) { Body::handoff_store(thr[t], t, exch.data() + ((t >> 5) | 1) * Cfg::Lay::SC, wm.data()); });
-          else half([&](int t) { if (pb(t) < batch) Body::combine_store_paired(thr[t], a, pbc(t), t, exch.data() + ((t >> 5) | 1) * Cfg::Lay::SC, chirp.data()); });
-        }
-      } else {
       for (int odd = 0; odd < 2; ++odd) {
         all([&](int t) { if (odd) Body::template load_half<true>(thr[t], a, bcl(t), t, exch.data(), twa.data(), chirp.data(), wm.data());
                          else Body::template load_half<false>(thr[t], a, bcl(t), t, exch.data(), twa.data(), chirp.data(), wm.data()); });
@@ -261,7 +243,6 @@ static int check_bluestein(const char* name, long n, double tol) {
         if (!odd) all([&](int t) { Body::stash_even(thr[t], t, stash.data()); });
       }
       all([&](int t) { if (bidx(t) < batch) Body::combine_store(stash.data(), thr[t], a, bcl(t), t, chirp.data(), wm.data()); });
-      }
     }
     double worst = 0;
     for (long b = 0; b < batch; ++b) {
@@ -571,8 +552,6 @@ int main() {
   bad += check_onchip<double, 16, 16, 16, 8>("onchip f64", 5e-15);
   bad += check_bluestein<float, 32, 11>("bluestein f32", 1009, 3e-6);
   bad += check_bluestein<float, 32, 11>("bluestein f32", 513, 3e-6);
-  bad += check_bluestein<float, 32, 4, true>("bluestein f32 (paired warps)", 1009, 3e-6);
-  bad += check_bluestein<float, 32, 4, true>("bluestein f32 (paired warps)", 600, 3e-6);
   bad += check_bluestein<float, 16, 8>("bluestein f32", 255, 3e-6);
   bad += check_bluestein<float, 8, 8>("bluestein f32", 37, 3e-6);
   bad += check_bluestein<double, 16, 8>("bluestein f64", 191, 1e-13);
