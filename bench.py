@@ -238,7 +238,7 @@ def run_distributed(args, rank, local_rank, world, barrier, log2n=None, steps=No
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     n_exchanges = 3 if natural else 2
     wire = plan.wire_bytes_per_exchange(8) * n_exchanges
-    exchange, chunks = plan.exchange, plan.chunks
+    exchange, chunks, fused = plan.exchange, plan.chunks, plan.fused
     plan.close()
     del x, s, cur, oth, out
     if rank != 0:
@@ -247,7 +247,9 @@ def run_distributed(args, rank, local_rank, world, barrier, log2n=None, steps=No
     peak, peak_src = measured_peak()
     # per GPU and step, read + write each: 2 FFT batches and 3 exchanges (one sweep each over NVLink peer memory;
     # pack + all_to_all + unpack = 3 sweeps with NCCL)
-    sweeps = 2 + n_exchanges * (1 if exchange == "peer" else 3)
+    # fused: the exchanges that follow row FFTs ride on the FFTs' stores -- exchange 1, then 2 (FFT + exchange)
+    # sweeps, or FFT + exchange and a plain FFT for transposed output
+    sweeps = 3 if fused else 2 + n_exchanges * (1 if exchange == "peer" else 3)
     local_bytes = blk * 8 * 2 * sweeps
     achieved = local_bytes / (ms_per_step * 1e-3) / 1e9
     return {
@@ -256,7 +258,12 @@ def run_distributed(args, rank, local_rank, world, barrier, log2n=None, steps=No
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS["c5"][3], "N": n, "n1": n1, "n2": n2,
-                   "parallelism": (f"block-distributed over {world} ranks, {n_exchanges} exchanges, each ONE transposing kernel storing "
+                   "parallelism": (f"block-distributed over {world} ranks, {n_exchanges} exchanges over NVLink peer memory (CUDA IPC), "
+                                   f"{n_exchanges - 1} of them folded into the last register stage of the row FFTs that precede "
+                                   "them (the FFT kernel stores straight into the peers' buffers), the first one a "
+                                   "transposing kernel; stream-ordered barriers between the steps"
+                                   if fused else
+                                   f"block-distributed over {world} ranks, {n_exchanges} exchanges, each ONE transposing kernel storing "
                                    "into the peers' buffers over NVLink (CUDA IPC) + a stream-ordered barrier"
                                    + (f"; the exchange of a row block overlaps the FFTs of the next ({chunks} blocks)"
                                       if chunks > 1 else "")
@@ -462,8 +469,9 @@ def main():
     ap.add_argument("--transposed-output", action="store_true",
                     help="c5 only: leave the result transposed (2 exchanges instead of 3)")
     ap.add_argument("--chunks", type=int, default=0, help="c5 only: row blocks per pipelined exchange (0 = plan default)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="c5 only: exchanges as one kernel over NVLink peer memory, or pack + NCCL all_to_all + unpack")
+    ap.add_argument("--exchange", default="peer", choices=["fused", "peer", "nccl"],
+                    help="c5 only: exchanges folded into the row FFTs' stores over NVLink peer memory, as one kernel "
+                         "each over peer memory, or pack + NCCL all_to_all + unpack")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

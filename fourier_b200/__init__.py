@@ -156,6 +156,24 @@ class Fft:
     def ifft(self, input, output):
         self.transform(input, output, Transform.Ifft)
 
+    # -- distributed six-step transform: row FFTs + exchange in one pass (csrc/dist_fft.cu) -----------------
+    def fft_rows_exchange(self, rows, outs, out_ld, out_off, forward=True, twiddle=None):
+        """FFT of the contiguous rows of the CUDA tensor `rows` (unscaled) whose last register stage stores the result
+        transposed into the buffers `outs` (a ctypes array of device pointers, one per destination rank):
+        outs[q][c*out_ld + out_off + r] = FFT(rows[r])[q*cb + c] * w_Ntot^{(row0 + r)*(q*cb + c)}, cb = size / len(outs);
+        twiddle = None or (row0, Ntot).  Two-pass plans only (raises NotImplementedError otherwise)."""
+        ptr, count, on_device, stream = self._describe(rows)
+        if not on_device:
+            raise ValueError("fft_rows_exchange needs CUDA tensors")
+        mode, row0, n_total = (0, 0, 0) if twiddle is None else ((1 if forward else 2), int(twiddle[0]), int(twiddle[1]))
+        rc = getattr(_lib.load(), f"fourier_b200_fft_rows_exchange_{self._t}")(
+            self._plan, ptr, count, int(bool(forward)), outs, len(outs), int(out_ld), int(out_off), mode, row0,
+            n_total, stream)
+        if rc == 801:
+            raise NotImplementedError(_lib.last_error())
+        if rc != 0:
+            raise RuntimeError(f"fft_rows_exchange failed (cuda error {rc}): {_lib.last_error()}")
+
     # -- the raw single-transform reference ABI (for the boundary tests) ------------------------------
     def c_transform(self, input, output, transform):
         pi, _, _, _ = self._describe(input)

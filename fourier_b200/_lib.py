@@ -27,7 +27,7 @@ EXTENSION_SYMBOLS = (
      "fourier_b200_path_name", "fourier_b200_last_error", "fourier_b200_version"]
     + [f"fourier_b200_{op}_{t}" for t in ("float", "double")
        for op in ("transform_batch", "transform_batch_async", "plan_info", "create_general", "fill_input",
-                  "transpose", "pack", "exchange", "swap_leading", "twiddle_rows", "plan_kernel")])
+                  "transpose", "pack", "exchange", "fft_rows_exchange", "swap_leading", "twiddle_rows", "plan_kernel")])
 
 
 def load():
@@ -62,6 +62,8 @@ def load():
                                                        ctypes.c_ulonglong, ctypes.c_ulonglong, vp]
         getattr(L, f"fourier_b200_exchange_{t}").argtypes = [vp, ctypes.POINTER(vp), ci, ci, sz, sz, sz, sz, sz, ci,
                                                            ctypes.c_ulonglong, ctypes.c_ulonglong, vp]
+        getattr(L, f"fourier_b200_fft_rows_exchange_{t}").argtypes = [vp, vp, sz, ci, ctypes.POINTER(vp), ci, sz, sz, ci,
+                                                                    ctypes.c_ulonglong, ctypes.c_ulonglong, vp]
         getattr(L, f"fourier_b200_swap_leading_{t}").argtypes = [vp, vp, sz, sz, sz, vp]
         getattr(L, f"fourier_b200_twiddle_rows_{t}").argtypes = [vp, sz, sz, ctypes.c_ulonglong, ctypes.c_ulonglong, ci, vp]
     L.fourier_b200_peer_alloc.argtypes = [sz, ctypes.POINTER(vp), ctypes.c_char_p]

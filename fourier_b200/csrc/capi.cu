@@ -101,6 +101,23 @@ int transform_async(const void* plan, const void* in, void* out, size_t batch, i
 }
 
 template <typename T>
+int rows_exchange(const void* plan, const void* in, size_t rows, int forward, void* const* outs, int nranks,
+                  size_t out_ld, size_t out_off, int twiddle, unsigned long long row0, unsigned long long n_total,
+                  void* stream) {
+  if (!plan || !in || !outs) { fb200::set_last_error("null argument"); return (int)cudaErrorInvalidValue; }
+  auto* p = const_cast<Plan<T>*>(static_cast<const Plan<T>*>(plan));
+  using C = typename Plan<T>::C;
+  try {
+    if (!device_pointers_aligned(in, in)) return (int)cudaErrorMisalignedAddress;
+    return (int)p->exec_rows_exchange((const C*)in, rows, forward != 0, outs, nranks, out_ld, out_off, twiddle, row0,
+                                      n_total, (cudaStream_t)stream);
+  } catch (...) {
+    fb200::set_last_error("rows_exchange threw");
+    return (int)cudaErrorUnknown;
+  }
+}
+
+template <typename T>
 int plan_info(const void* plan, fourier_b200_plan_info* out) {
   if (!plan || !out) return (int)cudaErrorInvalidValue;
   const auto* p = static_cast<const Plan<T>*>(plan);
@@ -247,6 +264,16 @@ int fourier_b200_exchange_double(const void* in, void* const* outs, int nranks, 
                                  unsigned long long n_total, void* stream) {
   return (int)fb200::launch_exchange<double>((const double2*)in, outs, nranks, me, rows, cb, ld, out_ld, out_off, twiddle,
                                              row0, n_total, (cudaStream_t)stream);
+}
+int fourier_b200_fft_rows_exchange_float(const fourier_fft_float* plan, const void* in, size_t rows, int forward,
+                                         void* const* outs, int nranks, size_t out_ld, size_t out_off, int twiddle,
+                                         unsigned long long row0, unsigned long long n_total, void* stream) {
+  return rows_exchange<float>(plan, in, rows, forward, outs, nranks, out_ld, out_off, twiddle, row0, n_total, stream);
+}
+int fourier_b200_fft_rows_exchange_double(const fourier_fft_double* plan, const void* in, size_t rows, int forward,
+                                          void* const* outs, int nranks, size_t out_ld, size_t out_off, int twiddle,
+                                          unsigned long long row0, unsigned long long n_total, void* stream) {
+  return rows_exchange<double>(plan, in, rows, forward, outs, nranks, out_ld, out_off, twiddle, row0, n_total, stream);
 }
 int fourier_b200_peer_alloc(size_t bytes, void** dev_ptr, void* handle64) { return (int)fb200::peer_alloc(bytes, dev_ptr, handle64); }
 int fourier_b200_peer_open(const void* handle64, void** dev_ptr) { return (int)fb200::peer_open(handle64, dev_ptr); }

@@ -1,0 +1,123 @@
+// dist_fft.cu -- row FFTs of the distributed six-step transform with the exchange folded into the store of their
+// last register stage (dist_kernels.cuh): pass 1 of the two-pass tile kernels as it is, pass 2 on tiles of C
+// adjacent transforms that store over NVLink peer memory.  Chunks alternate between the caller's stream and a
+// plan-owned one, each with its own L2-resident intermediate, so that pass 1 of one chunk (HBM reads, no NVLink
+// traffic) runs beside pass 2 of the other (NVLink stores).
+#include <algorithm>
+#include <cstdlib>
+
+#include "dist_kernels.cuh"
+#include "plan.h"
+#include "twopass_kernels.cuh"
+
+namespace fb200 {
+
+#define FB_CHECK(expr)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+      return _e;                                                                             \
+    }                                                                                        \
+  } while (0)
+
+namespace {
+
+template <typename T> struct RowsExchangeCall {
+  const cpx<T>* scratch; const void* twa; void* const* outs; int nranks; size_t groups, out_ld, out_off;
+  int twiddle, cb_shift; unsigned long long row0, n_total; bool fwd; cudaStream_t s;
+};
+
+template <class G, bool FWD, int TW, typename T>
+cudaError_t launch_rows_exchange(const RowsExchangeCall<T>& c) {
+  using Tile = typename G::template Tile2<FWD>;
+  using Body = dist::RowsExchangeBody<Tile, typename G::Lay2, G::N1, G::N2, TW>;
+  auto kernel = &dist::rows_exchange_kernel<Body, Tile, G::kMinBlocks2>;
+  static cudaError_t prepared =
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem2);
+  if (prepared != cudaSuccess) return prepared;
+  typename Body::Args a;
+  a.scratch = c.scratch;
+  a.twa = (const TwPair<T>*)c.twa;
+  for (int i = 0; i < kMaxPeers; ++i) a.outs.p[i] = i < c.nranks ? c.outs[i] : nullptr;
+  a.out_ld = c.out_ld; a.out_off = c.out_off; a.row0 = c.row0; a.n_total = c.n_total;
+  a.groups = (unsigned)c.groups; a.cb_shift = c.cb_shift;
+  kernel<<<(unsigned)(c.groups * (size_t)G::N1), Tile::THREADS, G::smem2, c.s>>>(a);
+  return cudaGetLastError();
+}
+
+template <class G, typename T> cudaError_t dispatch_rows_exchange(const RowsExchangeCall<T>& c) {
+  if (c.fwd) return c.twiddle ? launch_rows_exchange<G, true, 1>(c) : launch_rows_exchange<G, true, 0>(c);
+  return c.twiddle ? launch_rows_exchange<G, false, 2>(c) : launch_rows_exchange<G, false, 0>(c);
+}
+
+}  // namespace
+
+template <typename T>
+cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, void* const* outs, int nranks,
+                                        size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
+                                        unsigned long long n_total, cudaStream_t s) {
+  if (path_ != Path::kTwoPass || !fast_ops_) {
+    set_last_error("rows_exchange: the plan is not a two-pass plan (power-of-two sizes 2^11 .. 2^20 (f32), 2^9 .. 2^16 (f64))");
+    return cudaErrorNotSupported;
+  }
+  if (!in || !outs || nranks < 1 || nranks > kMaxPeers || (nranks & (nranks - 1)) || n_ % (size_t)nranks ||
+      twiddle < 0 || twiddle > 2 || (twiddle == 1 && !forward) || (twiddle == 2 && forward)) {
+    set_last_error("rows_exchange: bad arguments (ranks must be a power of two dividing the size; twiddle 1 goes with "
+                   "the forward, 2 with the inverse direction)");
+    return cudaErrorInvalidValue;
+  }
+  if (twiddle != 0 && (n_total == 0 || n_total > (1ull << 32) || row0 + rows > (1ull << 32))) {
+    set_last_error("rows_exchange: twiddle index out of range");
+    return cudaErrorInvalidValue;
+  }
+  if (rows == 0) return cudaSuccess;
+  const auto* ops = static_cast<const twopass::TwoPassOps<T>*>(fast_ops_);
+  int c2 = 0;
+  twopass::visit_config<T>(n_, [&](auto g) { c2 = decltype(g)::C2; });
+  if (c2 == 0 || rows % (size_t)c2) {
+    set_last_error("rows_exchange: the number of rows must be a multiple of " + std::to_string(c2));
+    return cudaErrorInvalidValue;
+  }
+  DeviceGuard guard(device_);
+  int cb_shift = 0;
+  while (((size_t)1 << cb_shift) < n_ / (size_t)nranks) ++cb_shift;
+  // chunks of whole tiles whose intermediate stays in L2; two of them in flight
+  size_t chunk = std::max<size_t>((size_t)c2, std::min(chunk_, rows) / (size_t)c2 * (size_t)c2);
+  const char* env = std::getenv("FOURIER_B200_DIST_OVERLAP");
+  const bool overlap = !(env && atoi(env) == 0) && rows > chunk;
+  FB_CHECK(work_.reserve((overlap ? 2 : 1) * chunk * n_ * sizeof(C)));
+  cudaStream_t lanes[2] = {s, s};
+  if (overlap) {
+    FB_CHECK(host_resources());
+    lanes[1] = streams_[0];
+    FB_CHECK(cudaEventRecord(events_[0], s));
+    FB_CHECK(cudaStreamWaitEvent(lanes[1], events_[0], 0));
+  }
+  launches_ = 0;
+  size_t i = 0;
+  for (size_t b0 = 0; b0 < rows; b0 += chunk, ++i) {
+    const size_t nb = std::min(chunk, rows - b0);
+    C* scratch = (C*)work_.data() + (overlap ? (i & 1) * chunk * n_ : 0);
+    cudaStream_t st = lanes[i & 1];
+    FB_CHECK(ops->pass1(in + b0 * n_, scratch, tw_a_.data(), (const C*)tw2_.data(), nb, forward, st));
+    RowsExchangeCall<T> c{scratch, tw_b_.data(), outs, nranks, nb / (size_t)c2, out_ld, out_off + b0, twiddle, cb_shift,
+                          row0 + b0, n_total, forward, st};
+    cudaError_t e = cudaErrorNotSupported;
+    twopass::visit_config<T>(n_, [&](auto g) { e = dispatch_rows_exchange<decltype(g)>(c); });
+    FB_CHECK(e);
+    launches_ += 2;
+  }
+  if (overlap) {
+    FB_CHECK(cudaEventRecord(events_[1], lanes[1]));
+    FB_CHECK(cudaStreamWaitEvent(s, events_[1], 0));
+  }
+  return cudaSuccess;
+}
+
+template cudaError_t Plan<float>::exec_rows_exchange(const C*, size_t, bool, void* const*, int, size_t, size_t, int,
+                                                     unsigned long long, unsigned long long, cudaStream_t);
+template cudaError_t Plan<double>::exec_rows_exchange(const C*, size_t, bool, void* const*, int, size_t, size_t, int,
+                                                      unsigned long long, unsigned long long, cudaStream_t);
+
+}  // namespace fb200

@@ -96,19 +96,6 @@ template <typename T> T scale_for(int code, size_t n) {
   }
 }
 
-struct DeviceGuard {
-  int prev = -1;
-  bool ok = true;
-  explicit DeviceGuard(int dev) {
-    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
-  }
-  ~DeviceGuard() {
-    int cur = -1;
-    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-  }
-};
-
 constexpr size_t kScratchTargetBytes = (size_t)512 << 20;  // per scratch buffer on the general path
 constexpr size_t kHostChunkBytes = (size_t)64 << 20;       // host-pointer pipeline granule
 constexpr size_t kHostSmallBytes = (size_t)1 << 20;        // below this a host call takes the single-stream latency path

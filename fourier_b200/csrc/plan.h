@@ -32,10 +32,26 @@ enum class Path : int {
 
 const char* path_name(Path p);
 
+constexpr int kMaxPeers = 16;   // ranks of one box (peer-memory exchange, exchange.cu / dist_fft.cu)
+
 // Selection rule of create_fft_f32/f64 (fourier/src/lib.rs:38-42 with autosort/mod.rs:104-117):
 // Autosort iff N = 2^a * 3^b (N >= 1), else Bluestein with inner size next_pow2(2N-1).
 bool is_23_smooth(size_t n);
 size_t bluestein_inner_size(size_t n);  // bluesteins.rs:110
+
+// Makes `dev` the current device for the lifetime of the guard.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
 
 // Grow-only device allocation.
 class DeviceBuffer {
@@ -87,6 +103,14 @@ class Plan {
   // Same on host memory (the reference ABI's case): staged H2D -> transform -> D2H through the
   // plan's own streams, chunked and pipelined; returns after the result is in `out`.
   cudaError_t exec_host(const C* in, C* out, size_t batch, int code);
+
+  // Distributed six-step transform (dist_fft.cu): batched FFT of `rows` contiguous rows of size() samples whose last
+  // register stage stores the result transposed, and optionally twiddled, straight into the destination ranks'
+  // buffers: outs[q][c * out_ld + out_off + r] = X_r[q * cb + c] * w_Ntot^{(row0 + r) * (q * cb + c)}, cb = size() / nranks
+  // (what launch_exchange() delivers after exec_device() on the same rows).  Two-pass sizes only; `in` is left intact.
+  cudaError_t exec_rows_exchange(const C* in, size_t rows, bool forward, void* const* outs, int nranks, size_t out_ld,
+                                 size_t out_off, int twiddle, unsigned long long row0, unsigned long long n_total,
+                                 cudaStream_t stream);
 
   // Number of kernel launches the last exec_* call issued (bench.py reports it).
   unsigned long long launches() const { return launches_; }
@@ -193,7 +217,6 @@ cudaError_t launch_twiddle_rows(cpx<T>* data, size_t rows, size_t cols, unsigned
                                 unsigned long long n_total, bool forward, cudaStream_t s);
 
 // exchange.cu: exchange step of the distributed transform over NVLink peer memory + CUDA-IPC plumbing
-constexpr int kMaxPeers = 16;
 template <typename T>
 cudaError_t launch_exchange(const cpx<T>* in, void* const* outs, int nranks, int me, size_t rows, size_t cb, size_t ld,
                             size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,

@@ -78,6 +78,7 @@ template <typename T, class S1, class S2, int MINB1, int MINB2>
 struct TwoPassG {
   static constexpr long N1 = S1::L, N2 = S2::L, N = N1 * N2;
   static constexpr int C1 = S1::C, C2 = S2::C;
+  static constexpr int kMinBlocks1 = MINB1, kMinBlocks2 = MINB2;
   // pass 1: FFT length N1 over n1 (stride N2), C1 adjacent columns; both stages "col fast"
   template <bool FWD> using Tile1 = TileFFT<T, S1::RA, S1::RB, S1::E, C1, FWD>;
   using Lay1 = ExLayout<S1::RA * C1 + S1::PAD, C1, 1>;
@@ -138,38 +139,49 @@ template <typename T, int R1, int R2, int C1, int C2, int PAD1, int MINB1, int M
 using TwoPass = TwoPassG<T, Shape<R1, R1, R1, C1, PAD1>, Shape<R2, R2, R2, C2, 1>, MINB1, MINB2>;
 
 // Supported sizes.  f32: 32x32 register stages (1024-point tiles); f64: 16x16 (256-point tiles).
-template <typename T> const TwoPassOps<T>* lookup(size_t n);
-template <> inline const TwoPassOps<float>* lookup<float>(size_t n) {
+// visit_config<T>(n, f) calls f with a value of the configuration type of size n (false when there is none): the one
+// list of sizes behind lookup() here and behind the distributed variant of pass 2 (dist_fft.cu).
+template <class F> bool visit_config_f32(size_t n, F&& f) {
   switch (n) {
     case (size_t)1 << 20: {
       const char* env = std::getenv("FOURIER_B200_TILE");  // experiment knob: columns per tile
-      if (env && atoi(env) == 16) return TwoPass<float, 32, 32, 16, 16, 0, 1, 1>::ops();
-      return TwoPass<float, 32, 32, 8, 8, 8, 2, 2>::ops();
+      if (env && atoi(env) == 16) f(TwoPass<float, 32, 32, 16, 16, 0, 1, 1>{});
+      else f(TwoPass<float, 32, 32, 8, 8, 8, 2, 2>{});
+      return true;
     }
-    case (size_t)1 << 11: return TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>::ops();
-    case (size_t)1 << 12: return TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>::ops();
-    case (size_t)1 << 13: return TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>::ops();
-    case (size_t)1 << 14: return TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>::ops();
-    case (size_t)1 << 15: return TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<16, 16, 16, 16, 1>, 4, 2>::ops();
-    case (size_t)1 << 16: return TwoPass<float, 16, 16, 16, 16, 0, 2, 2>::ops();
-    case (size_t)1 << 17: return TwoPassG<float, Shape<16, 16, 16, 16, 0>, Shape<16, 32, 32, 8, 1>, 2, 2>::ops();
-    case (size_t)1 << 19: return TwoPassG<float, Shape<16, 32, 32, 8, 8>, Shape<32, 32, 32, 8, 1>, 2, 2>::ops();
-    case (size_t)1 << 18: return TwoPass<float, 16, 32, 16, 8, 0, 2, 2>::ops();
-    default: return nullptr;
+    case (size_t)1 << 11: f(TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>{}); return true;
+    case (size_t)1 << 12: f(TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>{}); return true;
+    case (size_t)1 << 13: f(TwoPassG<float, Shape<8, 8, 8, 32, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>{}); return true;
+    case (size_t)1 << 14: f(TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>{}); return true;
+    case (size_t)1 << 15: f(TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<16, 16, 16, 16, 1>, 4, 2>{}); return true;
+    case (size_t)1 << 16: f(TwoPass<float, 16, 16, 16, 16, 0, 2, 2>{}); return true;
+    case (size_t)1 << 17: f(TwoPassG<float, Shape<16, 16, 16, 16, 0>, Shape<16, 32, 32, 8, 1>, 2, 2>{}); return true;
+    case (size_t)1 << 19: f(TwoPassG<float, Shape<16, 32, 32, 8, 8>, Shape<32, 32, 32, 8, 1>, 2, 2>{}); return true;
+    case (size_t)1 << 18: f(TwoPass<float, 16, 32, 16, 8, 0, 2, 2>{}); return true;
+    default: return false;
   }
 }
-template <> inline const TwoPassOps<double>* lookup<double>(size_t n) {
+template <class F> bool visit_config_f64(size_t n, F&& f) {
   switch (n) {
-    case (size_t)1 << 16: return TwoPass<double, 16, 16, 8, 8, 4, 2, 2>::ops();
-    case (size_t)1 << 9: return TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>::ops();
-    case (size_t)1 << 10: return TwoPassG<double, Shape<4, 8, 8, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>::ops();
-    case (size_t)1 << 11: return TwoPassG<double, Shape<4, 8, 8, 16, 0>, Shape<8, 8, 8, 16, 1>, 4, 4>::ops();
-    case (size_t)1 << 12: return TwoPass<double, 8, 8, 16, 16, 0, 4, 4>::ops();
-    case (size_t)1 << 13: return TwoPassG<double, Shape<8, 8, 8, 16, 0>, Shape<8, 16, 16, 8, 1>, 4, 2>::ops();
-    case (size_t)1 << 15: return TwoPassG<double, Shape<8, 16, 16, 8, 4>, Shape<16, 16, 16, 8, 1>, 2, 2>::ops();
-    case (size_t)1 << 14: return TwoPass<double, 8, 16, 16, 8, 0, 4, 2>::ops();
-    default: return nullptr;
+    case (size_t)1 << 16: f(TwoPass<double, 16, 16, 8, 8, 4, 2, 2>{}); return true;
+    case (size_t)1 << 9: f(TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>{}); return true;
+    case (size_t)1 << 10: f(TwoPassG<double, Shape<4, 8, 8, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>{}); return true;
+    case (size_t)1 << 11: f(TwoPassG<double, Shape<4, 8, 8, 16, 0>, Shape<8, 8, 8, 16, 1>, 4, 4>{}); return true;
+    case (size_t)1 << 12: f(TwoPass<double, 8, 8, 16, 16, 0, 4, 4>{}); return true;
+    case (size_t)1 << 13: f(TwoPassG<double, Shape<8, 8, 8, 16, 0>, Shape<8, 16, 16, 8, 1>, 4, 2>{}); return true;
+    case (size_t)1 << 15: f(TwoPassG<double, Shape<8, 16, 16, 8, 4>, Shape<16, 16, 16, 8, 1>, 2, 2>{}); return true;
+    case (size_t)1 << 14: f(TwoPass<double, 8, 16, 16, 8, 0, 4, 2>{}); return true;
+    default: return false;
   }
+}
+template <typename T, class F> bool visit_config(size_t n, F&& f) {
+  if constexpr (sizeof(T) == 4) return visit_config_f32(n, f);
+  else return visit_config_f64(n, f);
+}
+template <typename T> const TwoPassOps<T>* lookup(size_t n) {
+  const TwoPassOps<T>* o = nullptr;
+  visit_config<T>(n, [&](auto g) { o = decltype(g)::ops(); });
+  return o;
 }
 
 template <typename T, typename U>

@@ -66,14 +66,28 @@ class CudaBackend:
     def empty(self, samples):
         return self.torch.empty(samples, dtype=self.dtype, device="cuda")
 
-    def fft_rows(self, x, n, forward):
-        """In-place batched FFT over rows of length n (unscaled in both directions)."""
-        from . import Fft, Transform
+    def _plan(self, x, n):
+        from . import Fft
         key = (x.device.index, n)
         plan = self._plans.get(key)
         if plan is None:
             plan = self._plans[key] = Fft(n, self.real)
-        plan.transform_in_place(x.view(-1, n), Transform.Fft if forward else Transform.UnscaledIfft)
+        return plan
+
+    def fft_rows(self, x, n, forward):
+        """In-place batched FFT over rows of length n (unscaled in both directions)."""
+        from . import Transform
+        self._plan(x, n).transform_in_place(x.view(-1, n), Transform.Fft if forward else Transform.UnscaledIfft)
+
+    def can_fuse(self, x, n, rows):
+        """True if fft_rows_exchange() exists for rows of length n (two-pass plans, whole tiles of up to 32 rows)."""
+        return self._plan(x, n).info()["path_name"] == "twopass" and rows % 32 == 0
+
+    def fft_rows_exchange(self, src, table, world, rank, rows_loc, n, forward, twiddle):
+        """The FFTs of the rows_loc rows of length n of `src` and the exchange() of the result in one pass: the last
+        register stage of the transform stores straight into the peers' buffers (csrc/dist_kernels.cuh)."""
+        tw = None if twiddle is None else (twiddle[1], twiddle[2])
+        self._plan(src, n).fft_rows_exchange(src.view(rows_loc, n), table, world * rows_loc, rank * rows_loc, forward, tw)
 
     def transpose(self, src, dst, rows, cols):
         self._call("transpose", src.data_ptr(), dst.data_ptr(), 1, rows, cols, self._stream(src))
@@ -231,16 +245,18 @@ class DistributedFft:
     def __init__(self, n1, n2, rank, world, backend, group=None, chunks=None, exchange="nccl"):
         if n1 % world or n2 % world:
             raise ValueError("n1 and n2 must be divisible by the number of ranks")
-        if exchange not in ("nccl", "peer"):
-            raise ValueError("exchange must be 'nccl' or 'peer'")
+        if exchange not in ("nccl", "peer", "fused"):
+            raise ValueError("exchange must be 'nccl', 'peer' or 'fused'")
         self.n1, self.n2, self.n = n1, n2, n1 * n2
         self.rank, self.world, self.backend, self.group = rank, world, backend, group
         self.exchange = exchange if world > 1 else "nccl"
         # measured (profiles/r01_c5_variants_8gpu.json, r01_c5_breakdown.txt): 8 pieces is the best pipelining of
         # the NCCL formulation; on the peer-memory path the overlap gains nothing yet (1 = no pipelining)
-        self.chunks = max(1, int(chunks)) if chunks else (1 if self.exchange == "peer" else 8)
+        self.chunks = max(1, int(chunks)) if chunks else (8 if self.exchange == "nccl" else 1)
         self._send = self._recv = None
         self._bufs, self._tables = None, {}
+        # "fused": peer memory as well, and the exchanges that follow row FFTs are folded into the FFTs' last stage
+        self.fused, self.exchange = self.exchange == "fused", ("peer" if self.exchange == "fused" else self.exchange)
         if self.exchange == "peer":      # collective: every rank of the group constructs the plan
             self._bufs, tables = backend.peer_buffers(self.local_samples(), 2, rank, world, group)
             self._tables = {b.data_ptr(): t for b, t in zip(self._bufs, tables)}
@@ -312,6 +328,10 @@ class DistributedFft:
         its block is done; the receivers need every block of every rank, hence one barrier at the end."""
         be, torch = self.backend, self.backend.torch
         table = self._table(dst)
+        if fft_len and self.fused and be.can_fuse(src, fft_len, rows_loc):
+            be.fft_rows_exchange(src, table, self.world, self.rank, rows_loc, fft_len, forward, twiddle)
+            be.barrier(self.group)
+            return dst
         K = self._pieces(rows_loc) if fft_len else 1
         rows_k = rows_loc // K
         main, side = torch.cuda.current_stream(), be.side_stream()

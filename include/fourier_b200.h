@@ -113,6 +113,22 @@ int fourier_b200_exchange_float(const void *in_dev, void *const *outs, int nrank
 int fourier_b200_exchange_double(const void *in_dev, void *const *outs, int nranks, int me, size_t rows, size_t cb,
                                  size_t ld, size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
                                  unsigned long long n_total, void *cuda_stream);
+/* The row FFTs of a step AND the exchange that follows them as one pass over the data: `rows` contiguous rows of the
+ * plan's size N are transformed (unscaled; forward != 0: Fft, else UnscaledIfft) and the last register stage of the
+ * transform stores its results straight into the destination ranks' buffers, transposed and twiddled:
+ *   outs[q][c*out_ld + out_off + r] = FFT_N(in[r*N ..])[q*cb + c] * w_Ntot^{(row0+r)*(q*cb+c)},   cb = N / nranks
+ * i.e. what fourier_b200_transform_batch_async_* followed by fourier_b200_exchange_* delivers, with one kernel and
+ * one sweep over HBM less and the NVLink stores overlapping the butterflies.  Two-pass plans only (power-of-two N,
+ * 2^11 .. 2^20 f32 / 2^9 .. 2^16 f64); nranks a power of two; rows a multiple of 16 (8 for N >= 2^17); twiddle 0,
+ * 1 (with forward) or 2 (with inverse); `in` is left intact.  Returns cudaErrorNotSupported (801) for other plans. */
+int fourier_b200_fft_rows_exchange_float(const FB200_F *plan, const void *in_dev, size_t rows,
+                                         int forward, void *const *outs, int nranks, size_t out_ld, size_t out_off,
+                                         int twiddle, unsigned long long row0, unsigned long long n_total,
+                                         void *cuda_stream);
+int fourier_b200_fft_rows_exchange_double(const FB200_D *plan, const void *in_dev, size_t rows,
+                                          int forward, void *const *outs, int nranks, size_t out_ld, size_t out_off,
+                                          int twiddle, unsigned long long row0, unsigned long long n_total,
+                                          void *cuda_stream);
 /* Buffers other ranks of the box (one process per GPU) can store into: cudaMalloc + CUDA IPC.  `handle64` is
  * the 64-byte cudaIpcMemHandle_t to send to the peers (any transport), who open it with _peer_open. */
 int fourier_b200_peer_alloc(size_t bytes, void **dev_ptr, void *handle64);

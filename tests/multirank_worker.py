@@ -7,6 +7,7 @@ Checks, with REAL peer memory (CUDA IPC over NVLink) and real NCCL collectives b
   * peer mode re-entrancy: the result of call 1 is consumed while a deliberately delayed rank is still
     busy and the other ranks have already entered call 2 -- the entry barrier of transform() must keep the fast
     ranks from overwriting the slow rank's result buffer.
+  * DistributedFft(exchange="fused") (row FFTs whose last stage stores into the peers) at N = 2^23;
 Prints "MULTIRANK OK" on rank 0 when everything passed on every rank.
 """
 import os
@@ -101,6 +102,42 @@ err = float((gather(plan.transform(x, scratch)) - ref).abs().max()) / scale
 check("peer, 64 exchange blocks, 4 pipelined chunks", err < 1e-5, f"rel err {err:.3e}")
 plan.close()
 del os.environ["FOURIER_B200_EXCHANGE_BLOCKS"]
+
+# exchange="fused": the exchanges after the row FFTs are folded into the FFTs' last stage (csrc/dist_kernels.cuh);
+# needs two-pass row lengths, so N = 2^11 x 2^12 here; natural and transposed output, round trip, against the
+# single-GPU plan of 2^23 points and the stand-alone exchange kernel
+f1, f2 = 1 << 11, 1 << 12
+fn = f1 * f2
+fblk = fn // world
+ffull = torch.empty(fn, dtype=torch.complex64, device="cuda")
+fb.fill_input(ffull.view(1, fn))
+fref = torch.empty_like(ffull)
+fb.create_fft_f32(fn).transform(ffull.view(1, fn), fref.view(1, fn), fb.Transform.Fft)
+fscale = float(fref.abs().max())
+fref_t = fref.view(f2, f1).t().contiguous().view(-1)
+results = {}
+for mode in ("fused", "peer"):
+    be = CudaBackend("f32")
+    plan = DistributedFft(f1, f2, rank, world, be, exchange=mode)
+    x, scratch = plan.buffers()
+    if mode == "fused":
+        check("fused mode is taken", plan.fused and be.can_fuse(x, f1, f2 // world) and be.can_fuse(x, f2, f1 // world))
+    mine = ffull[rank * fblk:(rank + 1) * fblk]
+    for natural in (True, False):
+        x.copy_(mine)
+        got = gather(plan.transform(x, scratch, natural_order=natural))
+        err = float((got - (fref if natural else fref_t)).abs().max()) / fscale
+        check(f"{mode} 2^23 natural={natural} vs single-GPU plan", err < 1e-5, f"rel err {err:.3e}")
+        results[(mode, natural)] = got
+    x.copy_(mine)
+    out = plan.transform(x, scratch)
+    back = plan.transform(out, x if out is scratch else scratch, forward=False) / fn
+    rt = float((back - mine).abs().max())
+    check(f"{mode} 2^23 round trip", rt < 1e-4, f"abs err {rt:.3e}")
+    plan.close()
+for natural in (True, False):
+    d = float((results[("fused", natural)] - results[("peer", natural)]).abs().max()) / fscale
+    check(f"fused vs peer natural={natural}", d < 2e-6, f"rel diff {d:.3e}")
 
 bad = torch.tensor([len(failures)], device="cuda")
 dist.all_reduce(bad)

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "cta_kernels.cuh"
+#include "dist_kernels.cuh"
 #include "fused_kernels.cuh"
 #include "onchip_kernels.cuh"
 #include "twopass_kernels.cuh"
@@ -506,8 +507,77 @@ static int check_cta(const char* name, int n, bool chirp_mode, double tol) {
   return bad;
 }
 
+// ---- row FFTs with the exchange folded into the store of pass 2 (dist_kernels.cuh) -----------------------------
+// pass 1 of the configuration as it is, then RowsExchangeBody with P destination buffers in host memory; reference:
+// dst_q[c * out_ld + out_off + r] = FFT(row r)[q * cb + c] * w_Ntot^{(row0 + r) * (q * cb + c)}
+template <typename T, class Cfg, int TW>
+static int check_rows_exchange(const char* name, int P, double tol) {
+  constexpr bool FWD = TW != 2;
+  const long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
+  using Tile = typename Cfg::template Tile2<FWD>;
+  using Body = dist::RowsExchangeBody<Tile, typename Cfg::Lay2, Cfg::N1, Cfg::N2, TW>;
+  const long rows = 2 * Tile::C, cb = N / P;
+  const unsigned long long row0 = 12345, n_total = (unsigned long long)N * 4096, out_off = 3 * rows, out_ld = 5 * rows;
+  std::vector<cpx<T>> x((size_t)N * rows), scratch((size_t)N * rows);
+  fill<T>(x, 21 + TW);
+  const auto* ops = Cfg::ops();
+  auto twa1 = make_twa<T>(ops->ra1, ops->rb1), twa2 = make_twa<T>(ops->ra2, ops->rb2);
+  std::vector<cpx<T>> tw2(N);
+  for (long k1 = 0; k1 < N1; ++k1)
+    for (long c = 0; c < N2; ++c) {
+      double re, im;
+      host_twiddle((size_t)(k1 * c), (size_t)N, &re, &im);
+      tw2[k1 * N2 + c] = mk<T>((T)re, (T)im);
+    }
+  run_body<typename Cfg::template Body1<FWD>, typename Cfg::template Tile1<FWD>, typename Cfg::Lay1>(
+      Cfg::template args1<FWD>(x.data(), scratch.data(), twa1.data(), tw2.data()), rows * (N2 / Cfg::template Tile1<FWD>::C));
+  std::vector<std::vector<cpx<T>>> dst(P, std::vector<cpx<T>>((size_t)cb * out_ld, mk<T>((T)777, (T)777)));
+  typename Body::Args a;
+  a.scratch = scratch.data(); a.twa = twa2.data();
+  for (int q = 0; q < kMaxPeers; ++q) a.outs.p[q] = q < P ? dst[q].data() : nullptr;
+  a.out_ld = out_ld; a.out_off = out_off; a.row0 = row0; a.n_total = n_total; a.groups = (unsigned)(rows / Tile::C);
+  a.cb_shift = 0;
+  while ((1L << a.cb_shift) < cb) ++a.cb_shift;
+  run_body<Body, Tile, typename Cfg::Lay2>(a, (long)a.groups * N1);
+  double worst = 0, maxref = 0;
+  for (long r = 0; r < rows; ++r) {
+    std::vector<double> re(N), im(N);
+    for (long i = 0; i < N; ++i) { re[i] = x[(size_t)r * N + i].x; im[i] = x[(size_t)r * N + i].y; }
+    host_fft_pow2(re, im, !FWD);
+    for (long k = 0; k < N; ++k) {
+      double wr = 1, wi = 0;
+      if (TW) {
+        const unsigned long long m = (row0 + r) * (unsigned long long)k % n_total;
+        const double ang = 2 * M_PI * (double)m / (double)n_total;
+        wr = std::cos(ang); wi = TW == 1 ? -std::sin(ang) : std::sin(ang);
+      }
+      const double rr = re[k] * wr - im[k] * wi, ii = re[k] * wi + im[k] * wr;
+      const cpx<T> got = dst[k / cb][(size_t)(k % cb) * out_ld + out_off + r];
+      maxref = std::max(maxref, std::hypot(rr, ii));
+      worst = std::max(worst, std::hypot(got.x - rr, got.y - ii));
+    }
+  }
+  // nothing outside the chunk's columns may be written
+  long stray = 0;
+  for (int q = 0; q < P; ++q)
+    for (long c = 0; c < cb; ++c)
+      for (long j = 0; j < (long)out_ld; ++j)
+        if ((j < (long)out_off || j >= (long)out_off + rows) && dst[q][(size_t)c * out_ld + j].x != (T)777) ++stray;
+  const double rel = worst / maxref;
+  printf("%s rows+exchange (P=%d, twiddle %d): max rel err %.3e (tol %.1e), stray stores %ld %s\n", name, P, TW, rel, tol, stray,
+         rel < tol && stray == 0 ? "OK" : "FAIL");
+  return !(rel < tol && stray == 0);
+}
+
 int main() {
   int bad = 0;
+  bad += check_rows_exchange<float, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, 1>("f32 2^11", 4, 2e-6);
+  bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>, 1>("f32 2^14", 8, 2e-6);
+  bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>, 2>("f32 2^14", 2, 2e-6);
+  bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<16, 16, 16, 16, 1>, 4, 2>, 0>("f32 2^15", 8, 2e-6);
+  bad += check_rows_exchange<float, TwoPass<float, 16, 16, 16, 16, 0, 2, 2>, 1>("f32 2^16", 1, 2e-6);
+  bad += check_rows_exchange<double, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, 1>("f64 2^9", 4, 5e-15);
+  bad += check_rows_exchange<double, TwoPass<double, 8, 8, 16, 16, 0, 4, 4>, 2>("f64 2^12", 16, 5e-15);
   bad += check_cta<float>("cta f32", 243, false, 2e-6);
   bad += check_cta<float>("cta f32", 729, false, 2e-6);
   bad += check_cta<float>("cta f32", 2187, false, 3e-6);
