@@ -469,7 +469,7 @@ def main():
     ap.add_argument("--transposed-output", action="store_true",
                     help="c5 only: leave the result transposed (2 exchanges instead of 3)")
     ap.add_argument("--chunks", type=int, default=0, help="c5 only: row blocks per pipelined exchange (0 = plan default)")
-    ap.add_argument("--exchange", default="peer", choices=["fused", "peer", "nccl"],
+    ap.add_argument("--exchange", default="fused", choices=["fused", "peer", "nccl"],
                     help="c5 only: exchanges folded into the row FFTs' stores over NVLink peer memory, as one kernel "
                          "each over peer memory, or pack + NCCL all_to_all + unpack")
     args = ap.parse_args()

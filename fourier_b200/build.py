@@ -22,7 +22,7 @@ VERSION = "0.1.0"
 SONAME = "libfourier.so.0"
 REAL = f"libfourier.so.{VERSION}"
 
-SOURCES = ["plan.cu", "host_math.cu", "stockham_generic.cu", "onchip.cu", "cta_fft.cu", "twopass.cu", "synth.cu", "exchange.cu", "dist_fft.cu", "capi.cu"]
+SOURCES = ["plan.cu", "host_math.cu", "stockham_generic.cu", "onchip.cu", "cta_fft.cu", "twopass.cu", "synth.cu", "exchange.cu", "dist_fft.cu", "bigpow2.cu", "capi.cu"]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

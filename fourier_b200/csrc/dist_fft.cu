@@ -82,8 +82,14 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
   DeviceGuard guard(device_);
   int cb_shift = 0;
   while (((size_t)1 << cb_shift) < n_ / (size_t)nranks) ++cb_shift;
-  // chunks of whole tiles whose intermediate stays in L2; two of them in flight
-  size_t chunk = std::max<size_t>((size_t)c2, std::min(chunk_, rows) / (size_t)c2 * (size_t)c2);
+  // chunks of whole tiles, two of them in flight.  Measured on 2 B200s (N = 2^28, profiles/r02_c5_fused_ab_2gpu.txt):
+  // 16 MB chunks 3.60 ms per transform, 32 MB 3.23, 64 MB 3.07 -- NVLink, not the L2 residency of the intermediate,
+  // bounds this path, and longer kernels overlap better across the two streams.  FOURIER_B200_DIST_CHUNK_MB overrides.
+  size_t mb = 64;
+  if (const char* e = std::getenv("FOURIER_B200_DIST_CHUNK_MB")) mb = (size_t)std::max(1, atoi(e));
+  else if (const char* e2 = std::getenv("FOURIER_B200_CHUNK_MB")) mb = (size_t)std::max(1, atoi(e2));
+  const size_t want = std::max<size_t>(1, (mb << 20) / (n_ * sizeof(C)));
+  size_t chunk = std::max<size_t>((size_t)c2, std::min(want, rows) / (size_t)c2 * (size_t)c2);
   const char* env = std::getenv("FOURIER_B200_DIST_OVERLAP");
   const bool overlap = !(env && atoi(env) == 0) && rows > chunk;
   FB_CHECK(work_.reserve((overlap ? 2 : 1) * chunk * n_ * sizeof(C)));

@@ -41,6 +41,7 @@ const char* path_name(Path p) {
     case Path::kBluestein: return "bluestein";
     case Path::kBluesteinFused: return "bluestein_fused";
     case Path::kCta: return "onchip_cta";
+    case Path::kThreePass: return "threepass";
   }
   return "?";
 }
@@ -137,6 +138,7 @@ const char* Plan<T>::kernel_name() const {
     case Path::kBluestein: return "chirp / pointwise kernels around the inner plan's kernels";
     case Path::kBluesteinFused: return cta_chirp_ ? "cta::cta_fft_kernel (chirp mode)" : "onchip::bluestein_fused_kernel";
     case Path::kCta: return "cta::cta_fft_kernel";
+    case Path::kThreePass: return "outer::column_kernel + twopass::tile_kernel (pass 1) + dist::rows_exchange_kernel (transposed store)";
   }
   return "?";
 }
@@ -167,6 +169,8 @@ cudaError_t Plan<T>::init(size_t n, int device, bool allow_fast_paths) {
       // covers can be measured on it
       const char* tp = std::getenv("FOURIER_B200_TWOPASS");
       if (!(tp && atoi(tp) == 0) && init_twopass() == cudaSuccess) { path_ = Path::kTwoPass; return cudaSuccess; }
+      // beyond the two-pass sizes: an outer column pass around two-pass rows (bigpow2.cu)
+      if (!(tp && atoi(tp) == 0) && init_bigpow2() == cudaSuccess) { path_ = Path::kThreePass; return cudaSuccess; }
     }
     // everything else that fits two shared-memory buffers: one kernel, one HBM round trip
     if (allow_fast_paths && init_cta(n) == cudaSuccess) { path_ = Path::kCta; return cudaSuccess; }
@@ -284,6 +288,7 @@ cudaError_t Plan<T>::exec_device(const C* in, C* out, size_t batch, int code, cu
     case Path::kBluesteinFused:
       return cta_chirp_ ? exec_cta(in, out, batch, code, stream, true) : exec_bluestein_fused(in, out, batch, code, stream);
     case Path::kCta: return exec_cta(in, out, batch, code, stream, false);
+    case Path::kThreePass: return exec_bigpow2(in, out, batch, code, stream);
   }
   return cudaErrorUnknown;
 }

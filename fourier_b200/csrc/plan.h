@@ -28,6 +28,7 @@ enum class Path : int {
   kBluesteinFused = 5,  // chirp-z with the inner FFTs on chip, one kernel
   kCta = 6,             // whole transforms in shared memory, one CTA per group of transforms, all Stockham stages
                         // in one kernel ({2,3}-smooth N, pow2 N between the on-chip and two-pass kernels)
+  kThreePass = 7,       // pow2 N above the two-pass kernels: outer column pass + two-pass rows storing transposed
 };
 
 const char* path_name(Path p);
@@ -128,10 +129,12 @@ class Plan {
   cudaError_t exec_bluestein(const C* in, C* out, size_t batch, int code, cudaStream_t s);
   cudaError_t exec_bluestein_fused(const C* in, C* out, size_t batch, int code, cudaStream_t s);
   cudaError_t exec_cta(const C* in, C* out, size_t batch, int code, cudaStream_t s, bool chirp);
+  cudaError_t exec_bigpow2(const C* in, C* out, size_t batch, int code, cudaStream_t s);
 
   cudaError_t init_global_stages();
   cudaError_t init_onchip();
   cudaError_t init_twopass();
+  cudaError_t init_bigpow2();
   cudaError_t init_cta(size_t len);   // len = n_, or the Bluestein inner size
   cudaError_t init_bluestein(bool allow_fast_paths);
   cudaError_t init_bluestein_fused(const std::vector<double>& chirp_re, const std::vector<double>& chirp_im,

@@ -157,6 +157,16 @@ struct TileFFT {
       }
   }
 
+  // Same with strides known only at run time (outer column pass of the three-pass path, outer_kernels.cuh).
+  template <int MAP> FB_HD void load_rt(int t, const V* __restrict__ base, long ns, long cs) {
+    const int col = col_of<MAP>(t), u = u_of<MAP>(t);
+    const V* p = base + (long)col * cs + (long)u * ns;
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int i = 0; i < RA; ++i) v[a * RA + i] = p[(long)(TP * a + RB * i) * ns];
+  }
+
   // Same for a tile of C = 8 FFTs stored in 8 x 8 blocks: sample n of FFT `col` at (n / 8) * 64 + col * 8 + n % 8.
   template <int MAP, int HINT = 0> FB_HD void load_blocked(int t, const V* __restrict__ base) {
     static_assert(C == 8 && RB % 8 == 0 && TP % 8 == 0, "blocked tiles hold 8 FFTs");

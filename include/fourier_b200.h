@@ -58,7 +58,7 @@ int fourier_b200_transform_batch_async_double(FB200_PLAN_D *plan, const void *in
 /* Plan introspection (Fft::size, fourier-algorithms/src/fft.rs:45, and the chosen strategy). */
 struct fourier_b200_plan_info {
   size_t size;        /* transform length N */
-  int path;           /* 0 trivial, 1 onchip, 2 twopass, 3 global_stages, 4 bluestein, 5 bluestein_fused, 6 onchip_cta */
+  int path;           /* 0 trivial, 1 onchip, 2 twopass, 3 global_stages, 4 bluestein, 5 bluestein_fused, 6 onchip_cta, 7 threepass */
   size_t inner_size;  /* Bluestein inner length next_pow2(2N-1) (bluesteins.rs:110), else 0 */
   int inner_path;
   size_t n1, n2;      /* two-pass split N = n1*n2, else 0 */
@@ -119,7 +119,7 @@ int fourier_b200_exchange_double(const void *in_dev, void *const *outs, int nran
  *   outs[q][c*out_ld + out_off + r] = FFT_N(in[r*N ..])[q*cb + c] * w_Ntot^{(row0+r)*(q*cb+c)},   cb = N / nranks
  * i.e. what fourier_b200_transform_batch_async_* followed by fourier_b200_exchange_* delivers, with one kernel and
  * one sweep over HBM less and the NVLink stores overlapping the butterflies.  Two-pass plans only (power-of-two N,
- * 2^11 .. 2^20 f32 / 2^9 .. 2^16 f64); nranks a power of two; rows a multiple of 16 (8 for N >= 2^17); twiddle 0,
+ * 2^11 .. 2^20 f32 / 2^9 .. 2^16 f64); nranks a power of two; rows a multiple of the tile height (32 up to N = 2^12 (f32), 8 from 2^17, else 16); twiddle 0,
  * 1 (with forward) or 2 (with inverse); `in` is left intact.  Returns cudaErrorNotSupported (801) for other plans. */
 int fourier_b200_fft_rows_exchange_float(const FB200_F *plan, const void *in_dev, size_t rows,
                                          int forward, void *const *outs, int nranks, size_t out_ld, size_t out_off,

@@ -110,6 +110,48 @@ def test_large_sizes_vs_oracle(real, n):
         assert e < TOL[real], (n, code, e)
 
 
+@pytest.mark.parametrize("real,n", [("f32", 1 << 21), ("f32", 1 << 23), ("f32", 1 << 25), ("f64", 1 << 17),
+                                    ("f64", 1 << 19), ("f64", 1 << 21)])
+def test_three_pass_path_above_the_two_pass_sizes(real, n):
+    """Power-of-two N beyond the two-pass kernels: outer column pass + two-pass rows with a transposed store
+    (csrc/bigpow2.cu).  Every Transform code against the oracle, in place == out of place, batch == loop, the
+    independent per-stage path, and one launch count: 1 + 2 per chunk of rows."""
+    import torch
+    x = O.fill_input(2, n, NP[real], first_transform=5)
+    p = create(real, n)
+    assert p.info()["path_name"] == "threepass" and p.info()["n1"] * p.info()["n2"] == n
+    assert "column_kernel" in p.kernel_name()
+    first = None
+    for code in (T.Fft, T.Ifft, T.UnscaledIfft, T.SqrtScaledFft, T.SqrtScaledIfft):
+        got = gpu_transform(p, x, code)
+        e = rel_err(got, O.transform(x, int(code)))
+        print(f"N=2^{n.bit_length() - 1} {real} {code.name}: rel err {e:.3e}")
+        assert e < TOL[real], (n, code, e)
+        if code == T.Fft:
+            first = got
+    assert p.info()["last_launches"] <= 2 * (1 + 2 * 8)
+    xd = torch.from_numpy(x).cuda()
+    p.transform_in_place(xd, T.Fft)                       # in place, device pointers, batch of 2
+    assert np.array_equal(xd.cpu().numpy(), first)
+    single = np.empty_like(x[1])
+    p.c_transform(np.ascontiguousarray(x[1]), single, T.Fft)
+    assert np.array_equal(single, first[1])
+    if n <= 1 << 23:
+        gen = create(real, n, general=True)
+        assert gen.info()["path_name"] == "global_stages"
+        assert rel_err(first, gpu_transform(gen, x, T.Fft)) < TOL[real]
+
+
+@pytest.mark.parametrize("real,n", [("f32", 1_500_001), ("f64", 100_003)])
+def test_bluestein_around_a_three_pass_inner_plan(real, n):
+    """Bluestein sizes whose inner power of two (2^22 f32, 2^18 f64) lies above the two-pass kernels."""
+    x = O.fill_input(1, n, NP[real], first_transform=2)
+    p = create(real, n)
+    assert p.info()["path_name"] == "bluestein" and p.info()["inner_path_name"] == "threepass"
+    got = gpu_transform(p, x, T.Fft)
+    assert rel_err(got, truth_f64(x, int(T.Fft))) < TOL[real]
+
+
 @pytest.mark.parametrize("real", ["f32", "f64"])
 def test_random_sizes_all_paths(real):
     """60 pseudo-random sizes up to 40000 (primes, prime powers, {2,3}-smooth, odd composites): every path

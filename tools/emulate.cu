@@ -15,6 +15,7 @@
 #include "dist_kernels.cuh"
 #include "fused_kernels.cuh"
 #include "onchip_kernels.cuh"
+#include "outer_kernels.cuh"
 #include "twopass_kernels.cuh"
 
 #ifndef FB_PAD16
@@ -569,8 +570,59 @@ static int check_rows_exchange(const char* name, int P, double tol) {
   return !(rel < tol && stray == 0);
 }
 
+// ---- three-pass path (bigpow2.cu): outer column pass + two-pass rows with the transposed store ---------------------
+template <typename T, class SO, class Cfg, bool FWD>
+static int check_threepass(const char* name, double tol) {
+  const long Na = SO::L, Nb = Cfg::N, N = Na * Nb;
+  using TileO = TileFFT<T, SO::RA, SO::RB, SO::E, SO::C, FWD>;
+  using LayO = ExLayout<SO::RA * SO::C + SO::PAD, SO::C, 1>;
+  using BodyO = outer::ColumnBody<TileO, LayO>;
+  std::vector<cpx<T>> x(N), work(N), scratch(N), out(N);
+  fill<T>(x, 31 + FWD);
+  auto twao = make_twa<T>(SO::RA, SO::RB);
+  typename BodyO::Args ao;
+  ao.in = x.data(); ao.out = work.data(); ao.twa = twao.data(); ao.nb = Nb; ao.n_total = N; ao.tiles = (unsigned)(Nb / SO::C);
+  ao.scale = (T)0.5;
+  run_body<BodyO, TileO, LayO>(ao, Nb / SO::C);
+  const auto* ops = Cfg::ops();
+  auto twa1 = make_twa<T>(ops->ra1, ops->rb1), twa2 = make_twa<T>(ops->ra2, ops->rb2);
+  std::vector<cpx<T>> tw2(Nb);
+  for (long k1 = 0; k1 < Cfg::N1; ++k1)
+    for (long c = 0; c < Cfg::N2; ++c) {
+      double re, im;
+      host_twiddle((size_t)(k1 * c), (size_t)Nb, &re, &im);
+      tw2[k1 * Cfg::N2 + c] = mk<T>((T)re, (T)im);
+    }
+  run_body<typename Cfg::template Body1<FWD>, typename Cfg::template Tile1<FWD>, typename Cfg::Lay1>(
+      Cfg::template args1<FWD>(work.data(), scratch.data(), twa1.data(), tw2.data()), Na * (Cfg::N2 / Cfg::template Tile1<FWD>::C));
+  using Tile = typename Cfg::template Tile2<FWD>;
+  using Body = dist::RowsExchangeBody<Tile, typename Cfg::Lay2, Cfg::N1, Cfg::N2, 0>;
+  typename Body::Args a;
+  a.scratch = scratch.data(); a.twa = twa2.data();
+  for (int q = 0; q < kMaxPeers; ++q) a.outs.p[q] = q == 0 ? out.data() : nullptr;
+  a.out_ld = Na; a.out_off = 0; a.row0 = 0; a.n_total = 0; a.groups = (unsigned)(Na / Tile::C);
+  a.cb_shift = 0;
+  while ((1L << a.cb_shift) < Nb) ++a.cb_shift;
+  run_body<Body, Tile, typename Cfg::Lay2>(a, (long)a.groups * Cfg::N1);
+  std::vector<double> re(N), im(N);
+  for (long i = 0; i < N; ++i) { re[i] = x[i].x; im[i] = x[i].y; }
+  host_fft_pow2(re, im, !FWD);
+  double maxref = 0, maxerr = 0;
+  for (long i = 0; i < N; ++i) {
+    maxref = std::max(maxref, std::hypot(re[i] * 0.5, im[i] * 0.5));
+    maxerr = std::max(maxerr, std::hypot(out[i].x - re[i] * 0.5, out[i].y - im[i] * 0.5));
+  }
+  printf("%s three-pass %ld x %ld (%s): max rel err %.3e (tol %.1e) %s\n", name, Na, Nb, FWD ? "forward" : "inverse",
+         maxerr / maxref, tol, maxerr / maxref < tol ? "OK" : "FAIL");
+  return !(maxerr / maxref < tol);
+}
+
 int main() {
   int bad = 0;
+  bad += check_threepass<float, Shape<4, 8, 8, 32, 0>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, true>("f32 2^16", 2e-6);
+  bad += check_threepass<float, Shape<8, 16, 16, 16, 0>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, false>("f32 2^18", 2e-6);
+  bad += check_threepass<double, Shape<4, 4, 4, 16, 0>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, true>("f64 2^13", 5e-15);
+  bad += check_threepass<double, Shape<8, 16, 16, 8, 4>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, false>("f64 2^16", 5e-15);
   bad += check_rows_exchange<float, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, 1>("f32 2^11", 4, 2e-6);
   bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>, 1>("f32 2^14", 8, 2e-6);
   bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>, 2>("f32 2^14", 2, 2e-6);
