@@ -122,11 +122,9 @@ cudaError_t Plan<T>::exec_bigpow2(const C* in, C* out, size_t batch, int code, c
     const size_t nb = std::min(chunk, batch - b0);
     FB_CHECK(col->launch(in + b0 * n_, work, tw_a_.data(), n2_, nb, scale, fwd, s));
     ++launches_;
-    for (size_t b = 0; b < nb; ++b) {
-      void* dst = out + (b0 + b) * n_;
-      FB_CHECK(inner_->exec_rows_exchange(work + b * n_, n1_, fwd, &dst, 1, n1_, 0, 0, 0, 0, s));
-      launches_ += inner_->launches();
-    }
+    void* dst = out + b0 * n_;   // the rows of all nb transforms in one call: batch b is stored n_ elements further on
+    FB_CHECK(inner_->exec_rows_exchange(work, nb * n1_, fwd, &dst, 1, n1_, 0, 0, 0, 0, s, n1_, n_));
+    launches_ += inner_->launches();
   }
   return cudaSuccess;
 }

@@ -26,6 +26,7 @@ namespace {
 template <typename T> struct RowsExchangeCall {
   const cpx<T>* scratch; const void* twa; void* const* outs; int nranks; size_t groups, out_ld, out_off;
   int twiddle, cb_shift; unsigned long long row0, n_total; bool fwd; cudaStream_t s;
+  size_t r0, out_bs; int rb_shift;
 };
 
 template <class G, bool FWD, int TW, typename T>
@@ -42,6 +43,7 @@ cudaError_t launch_rows_exchange(const RowsExchangeCall<T>& c) {
   for (int i = 0; i < kMaxPeers; ++i) a.outs.p[i] = i < c.nranks ? c.outs[i] : nullptr;
   a.out_ld = c.out_ld; a.out_off = c.out_off; a.row0 = c.row0; a.n_total = c.n_total;
   a.groups = (unsigned)c.groups; a.cb_shift = c.cb_shift;
+  a.r0 = c.r0; a.out_bs = c.out_bs; a.rb_shift = c.rb_shift;
   kernel<<<(unsigned)(c.groups * (size_t)G::N1), Tile::THREADS, G::smem2, c.s>>>(a);
   return cudaGetLastError();
 }
@@ -56,7 +58,8 @@ template <class G, typename T> cudaError_t dispatch_rows_exchange(const RowsExch
 template <typename T>
 cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, void* const* outs, int nranks,
                                         size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
-                                        unsigned long long n_total, cudaStream_t s) {
+                                        unsigned long long n_total, cudaStream_t s, size_t rows_per_batch,
+                                        size_t out_batch_stride) {
   if (path_ != Path::kTwoPass || !fast_ops_) {
     set_last_error("rows_exchange: the plan is not a two-pass plan (power-of-two sizes 2^11 .. 2^20 (f32), 2^9 .. 2^16 (f64))");
     return cudaErrorNotSupported;
@@ -70,6 +73,14 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
   if (twiddle != 0 && (n_total == 0 || n_total > (1ull << 32) || row0 + rows > (1ull << 32))) {
     set_last_error("rows_exchange: twiddle index out of range");
     return cudaErrorInvalidValue;
+  }
+  int rb_shift = 63;
+  if (rows_per_batch) {
+    if ((rows_per_batch & (rows_per_batch - 1)) || rows % rows_per_batch) {
+      set_last_error("rows_exchange: rows per batch must be a power of two dividing the number of rows");
+      return cudaErrorInvalidValue;
+    }
+    for (rb_shift = 0; ((size_t)1 << rb_shift) < rows_per_batch; ++rb_shift) {}
   }
   if (rows == 0) return cudaSuccess;
   const auto* ops = static_cast<const twopass::TwoPassOps<T>*>(fast_ops_);
@@ -107,8 +118,8 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
     C* scratch = (C*)work_.data() + (overlap ? (i & 1) * chunk * n_ : 0);
     cudaStream_t st = lanes[i & 1];
     FB_CHECK(ops->pass1(in + b0 * n_, scratch, tw_a_.data(), (const C*)tw2_.data(), nb, forward, st));
-    RowsExchangeCall<T> c{scratch, tw_b_.data(), outs, nranks, nb / (size_t)c2, out_ld, out_off + b0, twiddle, cb_shift,
-                          row0 + b0, n_total, forward, st};
+    RowsExchangeCall<T> c{scratch, tw_b_.data(), outs, nranks, nb / (size_t)c2, out_ld, out_off, twiddle, cb_shift,
+                          row0, n_total, forward, st, b0, out_batch_stride, rb_shift};
     cudaError_t e = cudaErrorNotSupported;
     twopass::visit_config<T>(n_, [&](auto g) { e = dispatch_rows_exchange<decltype(g)>(c); });
     FB_CHECK(e);
@@ -122,8 +133,8 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
 }
 
 template cudaError_t Plan<float>::exec_rows_exchange(const C*, size_t, bool, void* const*, int, size_t, size_t, int,
-                                                     unsigned long long, unsigned long long, cudaStream_t);
+                                                     unsigned long long, unsigned long long, cudaStream_t, size_t, size_t);
 template cudaError_t Plan<double>::exec_rows_exchange(const C*, size_t, bool, void* const*, int, size_t, size_t, int,
-                                                      unsigned long long, unsigned long long, cudaStream_t);
+                                                      unsigned long long, unsigned long long, cudaStream_t, size_t, size_t);
 
 }  // namespace fb200

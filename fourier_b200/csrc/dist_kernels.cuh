@@ -8,6 +8,7 @@
 //
 //   rows r = 0 .. rows-1 of length N (this rank's rows of the row-distributed matrix), X_r = FFT_N(row r)
 //   dst_q[c * out_ld + out_off + r] = X_r[q * cb + c] * w_Ntot^{(row0 + r) * (q * cb + c)},   cb = N / P
+//   (rows in batches of R: dst_q[(r / R) * out_bs + c * out_ld + out_off + r % R], the three-pass path of bigpow2.cu)
 //
 // which is exactly what fourier_b200_exchange_* delivers after a batched FFT of the rows.  The store is contiguous
 // along r (the batch), so one tile takes the SAME intermediate row k1 of C ADJACENT TRANSFORMS (instead of C adjacent
@@ -52,6 +53,9 @@ struct RowsExchangeBody {
     unsigned long long out_off;    // destination column of the chunk's first transform
     unsigned long long row0;       // global row index of the chunk's first transform (twiddle)
     unsigned long long n_total;    // Ntot of the twiddle
+    unsigned long long r0;         // index of the chunk's first transform among the rows of the call
+    unsigned long long out_bs;     // three-pass path (bigpow2.cu): rows come in batches of 2^rb_shift (one batch = one
+    int rb_shift;                  //   long transform), batch b is stored out_bs elements further on; 63 = one batch
     unsigned groups;               // transforms of the chunk / C
     int cb_shift;                  // log2(cb): destination rank of output k is k >> cb_shift
   };
@@ -70,12 +74,13 @@ struct RowsExchangeBody {
     f.stage_b();
     const int col = Tile::template col_of<kMapCF>(t), u = Tile::template u_of<kMapCF>(t);
     const unsigned long long r = (unsigned long long)g * C + col;          // transform of the chunk
-    const unsigned long long dcol = a.out_off + r;
+    const unsigned long long rc = a.r0 + r;                                // ... of the call
+    const unsigned long long dcol = (rc >> a.rb_shift) * a.out_bs + a.out_off + (rc & ((1ull << a.rb_shift) - 1));
     const unsigned long long mask = (1ull << a.cb_shift) - 1;
     [[maybe_unused]] double sr = 1.0, si = 0.0;
     [[maybe_unused]] unsigned long long rg = 0;
     if constexpr (TW != 0) {
-      rg = (a.row0 + r) % a.n_total;
+      rg = (a.row0 + rc) % a.n_total;
       unit_root(rg * (unsigned long long)(N1 * RA) % a.n_total, a.n_total, &sr, &si);
       if (TW == 1) si = -si;
     }

@@ -109,9 +109,11 @@ class Plan {
   // register stage stores the result transposed, and optionally twiddled, straight into the destination ranks'
   // buffers: outs[q][c * out_ld + out_off + r] = X_r[q * cb + c] * w_Ntot^{(row0 + r) * (q * cb + c)}, cb = size() / nranks
   // (what launch_exchange() delivers after exec_device() on the same rows).  Two-pass sizes only; `in` is left intact.
+  // rows_per_batch != 0 (three-pass path): the rows come in batches of that many, batch b goes out_batch_stride
+  // elements further on: outs[q][b * out_batch_stride + c * out_ld + out_off + r % rows_per_batch].
   cudaError_t exec_rows_exchange(const C* in, size_t rows, bool forward, void* const* outs, int nranks, size_t out_ld,
                                  size_t out_off, int twiddle, unsigned long long row0, unsigned long long n_total,
-                                 cudaStream_t stream);
+                                 cudaStream_t stream, size_t rows_per_batch = 0, size_t out_batch_stride = 0);
 
   // Number of kernel launches the last exec_* call issued (bench.py reports it).
   unsigned long long launches() const { return launches_; }

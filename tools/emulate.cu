@@ -537,6 +537,7 @@ static int check_rows_exchange(const char* name, int P, double tol) {
   a.scratch = scratch.data(); a.twa = twa2.data();
   for (int q = 0; q < kMaxPeers; ++q) a.outs.p[q] = q < P ? dst[q].data() : nullptr;
   a.out_ld = out_ld; a.out_off = out_off; a.row0 = row0; a.n_total = n_total; a.groups = (unsigned)(rows / Tile::C);
+  a.r0 = 0; a.out_bs = 0; a.rb_shift = 63;
   a.cb_shift = 0;
   while ((1L << a.cb_shift) < cb) ++a.cb_shift;
   run_body<Body, Tile, typename Cfg::Lay2>(a, (long)a.groups * N1);
@@ -577,13 +578,14 @@ static int check_threepass(const char* name, double tol) {
   using TileO = TileFFT<T, SO::RA, SO::RB, SO::E, SO::C, FWD>;
   using LayO = ExLayout<SO::RA * SO::C + SO::PAD, SO::C, 1>;
   using BodyO = outer::ColumnBody<TileO, LayO>;
-  std::vector<cpx<T>> x(N), work(N), scratch(N), out(N);
+  const long B = 2;   // two long transforms in one call
+  std::vector<cpx<T>> x(B * N), work(B * N), scratch(B * N), out(B * N);
   fill<T>(x, 31 + FWD);
   auto twao = make_twa<T>(SO::RA, SO::RB);
   typename BodyO::Args ao;
   ao.in = x.data(); ao.out = work.data(); ao.twa = twao.data(); ao.nb = Nb; ao.n_total = N; ao.tiles = (unsigned)(Nb / SO::C);
   ao.scale = (T)0.5;
-  run_body<BodyO, TileO, LayO>(ao, Nb / SO::C);
+  run_body<BodyO, TileO, LayO>(ao, B * (Nb / SO::C));
   const auto* ops = Cfg::ops();
   auto twa1 = make_twa<T>(ops->ra1, ops->rb1), twa2 = make_twa<T>(ops->ra2, ops->rb2);
   std::vector<cpx<T>> tw2(Nb);
@@ -594,23 +596,27 @@ static int check_threepass(const char* name, double tol) {
       tw2[k1 * Cfg::N2 + c] = mk<T>((T)re, (T)im);
     }
   run_body<typename Cfg::template Body1<FWD>, typename Cfg::template Tile1<FWD>, typename Cfg::Lay1>(
-      Cfg::template args1<FWD>(work.data(), scratch.data(), twa1.data(), tw2.data()), Na * (Cfg::N2 / Cfg::template Tile1<FWD>::C));
+      Cfg::template args1<FWD>(work.data(), scratch.data(), twa1.data(), tw2.data()), B * Na * (Cfg::N2 / Cfg::template Tile1<FWD>::C));
   using Tile = typename Cfg::template Tile2<FWD>;
   using Body = dist::RowsExchangeBody<Tile, typename Cfg::Lay2, Cfg::N1, Cfg::N2, 0>;
   typename Body::Args a;
   a.scratch = scratch.data(); a.twa = twa2.data();
   for (int q = 0; q < kMaxPeers; ++q) a.outs.p[q] = q == 0 ? out.data() : nullptr;
-  a.out_ld = Na; a.out_off = 0; a.row0 = 0; a.n_total = 0; a.groups = (unsigned)(Na / Tile::C);
+  a.out_ld = Na; a.out_off = 0; a.row0 = 0; a.n_total = 0; a.groups = (unsigned)(B * Na / Tile::C);
+  a.r0 = 0; a.out_bs = N; a.rb_shift = 0;
+  while ((1L << a.rb_shift) < Na) ++a.rb_shift;
   a.cb_shift = 0;
   while ((1L << a.cb_shift) < Nb) ++a.cb_shift;
   run_body<Body, Tile, typename Cfg::Lay2>(a, (long)a.groups * Cfg::N1);
-  std::vector<double> re(N), im(N);
-  for (long i = 0; i < N; ++i) { re[i] = x[i].x; im[i] = x[i].y; }
-  host_fft_pow2(re, im, !FWD);
   double maxref = 0, maxerr = 0;
-  for (long i = 0; i < N; ++i) {
-    maxref = std::max(maxref, std::hypot(re[i] * 0.5, im[i] * 0.5));
-    maxerr = std::max(maxerr, std::hypot(out[i].x - re[i] * 0.5, out[i].y - im[i] * 0.5));
+  for (long bb = 0; bb < B; ++bb) {
+    std::vector<double> re(N), im(N);
+    for (long i = 0; i < N; ++i) { re[i] = x[bb * N + i].x; im[i] = x[bb * N + i].y; }
+    host_fft_pow2(re, im, !FWD);
+    for (long i = 0; i < N; ++i) {
+      maxref = std::max(maxref, std::hypot(re[i] * 0.5, im[i] * 0.5));
+      maxerr = std::max(maxerr, std::hypot(out[bb * N + i].x - re[i] * 0.5, out[bb * N + i].y - im[i] * 0.5));
+    }
   }
   printf("%s three-pass %ld x %ld (%s): max rel err %.3e (tol %.1e) %s\n", name, Na, Nb, FWD ? "forward" : "inverse",
          maxerr / maxref, tol, maxerr / maxref < tol ? "OK" : "FAIL");
