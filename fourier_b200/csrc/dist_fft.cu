@@ -1,10 +1,11 @@
 // dist_fft.cu -- row FFTs of the distributed six-step transform with the exchange folded into the store of their
 // last register stage (dist_kernels.cuh): pass 1 of the two-pass tile kernels as it is, pass 2 on tiles of C
 // adjacent transforms that store over NVLink peer memory.  Chunks alternate between the caller's stream and a
-// plan-owned one, each with its own L2-resident intermediate, so that pass 1 of one chunk (HBM reads, no NVLink
-// traffic) runs beside pass 2 of the other (NVLink stores).
+// plan-owned ones (lanes), each with its own intermediate, so that pass 1 of one chunk (HBM reads, no NVLink
+// traffic) runs beside pass 2 of another (NVLink stores).
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "dist_kernels.cuh"
 #include "plan.h"
@@ -29,13 +30,35 @@ template <typename T> struct RowsExchangeCall {
   size_t r0, out_bs; int rb_shift;
 };
 
-template <class G, bool FWD, int TW, typename T>
+// Tiles of twice as many transforms where the configuration's pass-2 tile has 16 (f32) / 8 (f64): a warp's store is then
+// one 256-byte run instead of two 128-byte pieces (NVLink moves 256-byte packets: measured 2 B200s, N = 2^28 ...).
+// Paddings are the bank-conflict-free ones (tools/emulate.cu).
+template <class S, typename T> struct WideShape { using type = S; };
+template <> struct WideShape<twopass::Shape<8, 16, 16, 16, 2>, float> { using type = twopass::Shape<8, 16, 16, 32, 2>; };
+template <> struct WideShape<twopass::Shape<16, 16, 16, 16, 1>, float> { using type = twopass::Shape<16, 16, 16, 32, 1>; };
+template <> struct WideShape<twopass::Shape<8, 16, 16, 8, 1>, double> { using type = twopass::Shape<8, 16, 16, 16, 1>; };
+template <> struct WideShape<twopass::Shape<16, 16, 16, 8, 1>, double> { using type = twopass::Shape<16, 16, 16, 16, 1>; };
+
+template <class G, bool WIDE, typename T> struct ExchangeTile {
+  using S = typename std::conditional<WIDE, typename WideShape<typename G::Shape2, T>::type, typename G::Shape2>::type;
+  template <bool FWD> using Tile = TileFFT<T, S::RA, S::RB, S::E, S::C, FWD>;
+  using Lay = ExLayout<S::RA * S::C + S::PAD, S::C, 1>;
+  static constexpr int C = S::C;
+  static constexpr size_t smem = sizeof(cpx<T>) * Tile<true>::template smem_elems<Lay>();
+  // resident CTAs per SM: the configuration's pass-2 setting scaled to the tile's threads
+  static constexpr int kMinBlocks = (G::kMinBlocks2 * G::C2 + C - 1) / C;
+};
+
+// MORE: resident CTAs per SM beyond the configuration's pass-2 setting (the kernel waits on L2 / NVLink, not on
+// registers: ptxas fits 80 instead of 112 registers per thread without spilling)
+template <class G, bool FWD, int TW, int MORE, bool WIDE, typename T>
 cudaError_t launch_rows_exchange(const RowsExchangeCall<T>& c) {
-  using Tile = typename G::template Tile2<FWD>;
-  using Body = dist::RowsExchangeBody<Tile, typename G::Lay2, G::N1, G::N2, TW>;
-  auto kernel = &dist::rows_exchange_kernel<Body, Tile, G::kMinBlocks2>;
+  using X = ExchangeTile<G, WIDE, T>;
+  using Tile = typename X::template Tile<FWD>;
+  using Body = dist::RowsExchangeBody<Tile, typename X::Lay, G::N1, G::N2, TW>;
+  auto kernel = &dist::rows_exchange_kernel<Body, Tile, X::kMinBlocks + (WIDE ? MORE / 2 : MORE)>;
   static cudaError_t prepared =
-      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smem2);
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X::smem);
   if (prepared != cudaSuccess) return prepared;
   typename Body::Args a;
   a.scratch = c.scratch;
@@ -44,13 +67,18 @@ cudaError_t launch_rows_exchange(const RowsExchangeCall<T>& c) {
   a.out_ld = c.out_ld; a.out_off = c.out_off; a.row0 = c.row0; a.n_total = c.n_total;
   a.groups = (unsigned)c.groups; a.cb_shift = c.cb_shift;
   a.r0 = c.r0; a.out_bs = c.out_bs; a.rb_shift = c.rb_shift;
-  kernel<<<(unsigned)(c.groups * (size_t)G::N1), Tile::THREADS, G::smem2, c.s>>>(a);
+  kernel<<<(unsigned)(c.groups * (size_t)G::N1), Tile::THREADS, X::smem, c.s>>>(a);
   return cudaGetLastError();
 }
 
-template <class G, typename T> cudaError_t dispatch_rows_exchange(const RowsExchangeCall<T>& c) {
-  if (c.fwd) return c.twiddle ? launch_rows_exchange<G, true, 1>(c) : launch_rows_exchange<G, true, 0>(c);
-  return c.twiddle ? launch_rows_exchange<G, false, 2>(c) : launch_rows_exchange<G, false, 0>(c);
+template <class G, bool WIDE, typename T> cudaError_t dispatch_rows_exchange(const RowsExchangeCall<T>& c) {
+  constexpr int MORE = 2;   // +1 .. 6 % on the three-pass path, neutral on the distributed one (gpurun_out/occ_ab.log)
+  if (c.fwd) return c.twiddle ? launch_rows_exchange<G, true, 1, MORE, WIDE>(c) : launch_rows_exchange<G, true, 0, MORE, WIDE>(c);
+  return c.twiddle ? launch_rows_exchange<G, false, 2, MORE, WIDE>(c) : launch_rows_exchange<G, false, 0, MORE, WIDE>(c);
+}
+bool wide_wanted() {
+  static const bool w = [] { const char* e = std::getenv("FOURIER_B200_DIST_WIDE"); return !e || atoi(e) != 0; }();
+  return w;
 }
 
 }  // namespace
@@ -84,8 +112,14 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
   }
   if (rows == 0) return cudaSuccess;
   const auto* ops = static_cast<const twopass::TwoPassOps<T>*>(fast_ops_);
-  int c2 = 0;
-  twopass::visit_config<T>(n_, [&](auto g) { c2 = decltype(g)::C2; });
+  int c2 = 0, c2w = 0;
+  twopass::visit_config<T>(n_, [&](auto g) {
+    c2 = decltype(g)::C2;
+    c2w = ExchangeTile<decltype(g), true, T>::C;
+  });
+  const bool wide = wide_wanted() && c2w != c2 && rows % (size_t)c2w == 0 &&
+                    (rows_per_batch == 0 || rows_per_batch % (size_t)c2w == 0);
+  if (wide) c2 = c2w;
   if (c2 == 0 || rows % (size_t)c2) {
     set_last_error("rows_exchange: the number of rows must be a multiple of " + std::to_string(c2));
     return cudaErrorInvalidValue;
@@ -101,33 +135,41 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
   else if (const char* e2 = std::getenv("FOURIER_B200_CHUNK_MB")) mb = (size_t)std::max(1, atoi(e2));
   const size_t want = std::max<size_t>(1, (mb << 20) / (n_ * sizeof(C)));
   size_t chunk = std::max<size_t>((size_t)c2, std::min(want, rows) / (size_t)c2 * (size_t)c2);
-  const char* env = std::getenv("FOURIER_B200_DIST_OVERLAP");
-  const bool overlap = !(env && atoi(env) == 0) && rows > chunk;
-  FB_CHECK(work_.reserve((overlap ? 2 : 1) * chunk * n_ * sizeof(C)));
-  cudaStream_t lanes[2] = {s, s};
-  if (overlap) {
+  // lanes: chunks rotate over the caller's stream and up to three plan-owned ones, each with its own intermediate
+  int nlanes = 2;
+  if (const char* env = std::getenv("FOURIER_B200_DIST_LANES")) nlanes = std::min(4, std::max(1, atoi(env)));
+  if (const char* env = std::getenv("FOURIER_B200_DIST_OVERLAP")) { if (atoi(env) == 0) nlanes = 1; }
+  nlanes = (int)std::min<size_t>((size_t)nlanes, (rows + chunk - 1) / chunk);
+  FB_CHECK(work_.reserve((size_t)nlanes * chunk * n_ * sizeof(C)));
+  cudaStream_t lanes[4] = {s, s, s, s};
+  if (nlanes > 1) {
     FB_CHECK(host_resources());
-    lanes[1] = streams_[0];
     FB_CHECK(cudaEventRecord(events_[0], s));
-    FB_CHECK(cudaStreamWaitEvent(lanes[1], events_[0], 0));
+    for (int l = 1; l < nlanes; ++l) {
+      lanes[l] = streams_[l - 1];
+      FB_CHECK(cudaStreamWaitEvent(lanes[l], events_[0], 0));
+    }
   }
   launches_ = 0;
   size_t i = 0;
   for (size_t b0 = 0; b0 < rows; b0 += chunk, ++i) {
     const size_t nb = std::min(chunk, rows - b0);
-    C* scratch = (C*)work_.data() + (overlap ? (i & 1) * chunk * n_ : 0);
-    cudaStream_t st = lanes[i & 1];
+    const int lane = (int)(i % (size_t)nlanes);
+    C* scratch = (C*)work_.data() + (size_t)lane * chunk * n_;
+    cudaStream_t st = lanes[lane];
     FB_CHECK(ops->pass1(in + b0 * n_, scratch, tw_a_.data(), (const C*)tw2_.data(), nb, forward, st));
     RowsExchangeCall<T> c{scratch, tw_b_.data(), outs, nranks, nb / (size_t)c2, out_ld, out_off, twiddle, cb_shift,
                           row0, n_total, forward, st, b0, out_batch_stride, rb_shift};
     cudaError_t e = cudaErrorNotSupported;
-    twopass::visit_config<T>(n_, [&](auto g) { e = dispatch_rows_exchange<decltype(g)>(c); });
+    twopass::visit_config<T>(n_, [&](auto g) {
+      e = wide ? dispatch_rows_exchange<decltype(g), true>(c) : dispatch_rows_exchange<decltype(g), false>(c);
+    });
     FB_CHECK(e);
     launches_ += 2;
   }
-  if (overlap) {
-    FB_CHECK(cudaEventRecord(events_[1], lanes[1]));
-    FB_CHECK(cudaStreamWaitEvent(s, events_[1], 0));
+  for (int l = 1; l < nlanes; ++l) {
+    FB_CHECK(cudaEventRecord(events_[l], lanes[l]));
+    FB_CHECK(cudaStreamWaitEvent(s, events_[l], 0));
   }
   return cudaSuccess;
 }

@@ -79,6 +79,8 @@ struct TwoPassG {
   static constexpr long N1 = S1::L, N2 = S2::L, N = N1 * N2;
   static constexpr int C1 = S1::C, C2 = S2::C;
   static constexpr int kMinBlocks1 = MINB1, kMinBlocks2 = MINB2;
+  using Shape1 = S1;
+  using Shape2 = S2;
   // pass 1: FFT length N1 over n1 (stride N2), C1 adjacent columns; both stages "col fast"
   template <bool FWD> using Tile1 = TileFFT<T, S1::RA, S1::RB, S1::E, C1, FWD>;
   using Lay1 = ExLayout<S1::RA * C1 + S1::PAD, C1, 1>;

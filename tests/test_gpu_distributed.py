@@ -95,7 +95,9 @@ def test_peer_exchange_kernel_persistent_variant(monkeypatch):
 
 
 @pytest.mark.parametrize("real,n,P,rows_loc", [("f32", 1 << 14, 4, 64), ("f32", 1 << 11, 2, 96), ("f32", 1 << 16, 8, 48),
-                                               ("f32", 1 << 20, 2, 16), ("f64", 1 << 12, 4, 32), ("f64", 1 << 16, 2, 24)])
+                                               ("f32", 1 << 20, 2, 16), ("f64", 1 << 12, 4, 32), ("f64", 1 << 16, 2, 24),
+                                               # 64 / 32 rows: tiles of 32 (f32) / 16 (f64) transforms, 256-byte store runs
+                                               ("f32", 1 << 16, 4, 64), ("f64", 1 << 16, 4, 32), ("f32", 1 << 14, 2, 48)])
 @pytest.mark.parametrize("forward", [True, False])
 @pytest.mark.parametrize("twiddle", [False, True])
 def test_rows_fft_with_fused_exchange_matches_fft_then_exchange(real, n, P, rows_loc, forward, twiddle):

@@ -511,12 +511,16 @@ static int check_cta(const char* name, int n, bool chirp_mode, double tol) {
 // ---- row FFTs with the exchange folded into the store of pass 2 (dist_kernels.cuh) -----------------------------
 // pass 1 of the configuration as it is, then RowsExchangeBody with P destination buffers in host memory; reference:
 // dst_q[c * out_ld + out_off + r] = FFT(row r)[q * cb + c] * w_Ntot^{(row0 + r) * (q * cb + c)}
-template <typename T, class Cfg, int TW>
+// SW: shape of the tile (default: the configuration's pass-2 shape; dist_fft.cu also uses tiles of twice as many
+// transforms, WideShape)
+template <typename T, class Cfg, int TW, class SW = typename Cfg::Shape2>
 static int check_rows_exchange(const char* name, int P, double tol) {
   constexpr bool FWD = TW != 2;
   const long N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2;
-  using Tile = typename Cfg::template Tile2<FWD>;
-  using Body = dist::RowsExchangeBody<Tile, typename Cfg::Lay2, Cfg::N1, Cfg::N2, TW>;
+  using Tile = TileFFT<T, SW::RA, SW::RB, SW::E, SW::C, FWD>;
+  using LayX = ExLayout<SW::RA * SW::C + SW::PAD, SW::C, 1>;
+  report_conflicts<Tile, LayX, true>("exchange tile");
+  using Body = dist::RowsExchangeBody<Tile, LayX, Cfg::N1, Cfg::N2, TW>;
   const long rows = 2 * Tile::C, cb = N / P;
   const unsigned long long row0 = 12345, n_total = (unsigned long long)N * 4096, out_off = 3 * rows, out_ld = 5 * rows;
   std::vector<cpx<T>> x((size_t)N * rows), scratch((size_t)N * rows);
@@ -540,7 +544,7 @@ static int check_rows_exchange(const char* name, int P, double tol) {
   a.r0 = 0; a.out_bs = 0; a.rb_shift = 63;
   a.cb_shift = 0;
   while ((1L << a.cb_shift) < cb) ++a.cb_shift;
-  run_body<Body, Tile, typename Cfg::Lay2>(a, (long)a.groups * N1);
+  run_body<Body, Tile, LayX>(a, (long)a.groups * N1);
   double worst = 0, maxref = 0;
   for (long r = 0; r < rows; ++r) {
     std::vector<double> re(N), im(N);
@@ -636,6 +640,11 @@ int main() {
   bad += check_rows_exchange<float, TwoPass<float, 16, 16, 16, 16, 0, 2, 2>, 1>("f32 2^16", 1, 2e-6);
   bad += check_rows_exchange<double, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, 1>("f64 2^9", 4, 5e-15);
   bad += check_rows_exchange<double, TwoPass<double, 8, 8, 16, 16, 0, 4, 4>, 2>("f64 2^12", 16, 5e-15);
+  // tiles of twice as many transforms (256-byte store runs), as dist_fft.cu's WideShape selects them
+  bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>, 1, Shape<8, 16, 16, 32, 2>>("f32 2^14 wide", 8, 2e-6);
+  bad += check_rows_exchange<float, TwoPass<float, 16, 16, 16, 16, 0, 2, 2>, 2, Shape<16, 16, 16, 32, 1>>("f32 2^16 wide", 4, 2e-6);
+  bad += check_rows_exchange<double, TwoPassG<double, Shape<8, 8, 8, 16, 0>, Shape<8, 16, 16, 8, 1>, 4, 2>, 1, Shape<8, 16, 16, 16, 1>>("f64 2^13 wide", 2, 5e-15);
+  bad += check_rows_exchange<double, TwoPass<double, 16, 16, 8, 8, 4, 2, 2>, 0, Shape<16, 16, 16, 16, 1>>("f64 2^16 wide", 8, 5e-15);
   bad += check_cta<float>("cta f32", 243, false, 2e-6);
   bad += check_cta<float>("cta f32", 729, false, 2e-6);
   bad += check_cta<float>("cta f32", 2187, false, 3e-6);
