@@ -133,6 +133,16 @@ def cpu_baseline(n, real, seconds_target=12.0, threads=None):
                       f"{sec:.2f} s; oracle/ = C restatement of the reference algorithm (rustc absent)"}
 
 
+def workload_config(desc, n, batch, world, real):
+    """The `config` of a batched workload: identical in the CUDA arm and in the --impl reference arm (the driver
+    compares them); what is specific to an implementation goes into its own keys (`plan`, `cpu_baseline`)."""
+    bps = 16 if real == "f32" else 32
+    return {"workload": desc, "N": n, "batch_per_gpu": batch, "transform": "Fft (forward, out of place)",
+            "l2": "inputs larger than L2 (no flush needed)" if batch * n * bps // 2 > (256 << 20)
+            else "inputs smaller than L2: numbers are L2-warm",
+            "parallelism": f"batch-sharded x{world}, no collective"}
+
+
 def run_reference(args, n, batch, real, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port), host cores."""
     if rank != 0:
@@ -161,9 +171,9 @@ def run_reference(args, n, batch, real, rank, world):
         "unit": "complex samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": real, "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][3], "N": n, "batch_per_gpu": batch,
-                   "note": "reference CPU algorithm (oracle port: rustc/cargo absent from the image), "
-                           "all host threads, bounded sample per step"},
+        "config": workload_config(WORKLOADS[args.workload][3], n, batch, world, real),
+        "note": "reference CPU algorithm (oracle port: rustc/cargo absent from the image), all host threads, bounded "
+                "sample of the workload per step",
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "complex samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -215,7 +225,8 @@ def run_distributed(args, rank, local_rank, world, barrier, log2n=None, steps=No
     n1, n2 = 1 << (k - k2), 1 << k2
     n = n1 * n2
     blk = n // world
-    plan = DistributedFft(n1, n2, rank, world, CudaBackend("f32"), exchange=args.exchange, chunks=args.chunks or None)
+    be = CudaBackend("f32")
+    plan = DistributedFft(n1, n2, rank, world, be, exchange=args.exchange, chunks=args.chunks or None)
     x, s = plan.buffers()
     fb.fill_input(x.view(1, blk), first_transform=rank)
     cur, oth = x, s
@@ -238,6 +249,9 @@ def run_distributed(args, rank, local_rank, world, barrier, log2n=None, steps=No
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     n_exchanges = 3 if natural else 2
     wire = plan.wire_bytes_per_exchange(8) * n_exchanges
+    be.launches = 0          # one more, untimed transform to count this library's kernel launches per step
+    out = plan.transform(cur, oth, natural_order=natural)
+    launches_per_step, be.launches = be.launches, None
     exchange, chunks, fused = plan.exchange, plan.chunks, plan.fused
     plan.close()
     del x, s, cur, oth, out
@@ -278,7 +292,7 @@ def run_distributed(args, rank, local_rank, world, barrier, log2n=None, steps=No
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src,
                      "note": f"local sweeps only: {sweeps} read+write sweeps of the rank's block per step"},
-        "gpu_launches": None, "clocks": clocks.summary(),
+        "gpu_launches": launches_per_step * steps, "clocks": clocks.summary(),
     }
 
 
@@ -347,11 +361,8 @@ def run_batched(args, workload, batch, rank, local_rank, world, barrier, steps, 
             "metric": "batched 1D FFT complex-samples/sec", "value": value, "unit": "complex samples/s",
             "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": real, "data": "synthetic",
-            "config": {"workload": desc, "N": n, "batch_per_gpu": batch, "transform": "Fft (forward, out of place)",
-                       "path": info["path_name"], "inner_path": info["inner_path_name"],
-                       "l2": "inputs larger than L2 (no flush needed)" if batch * n * bps // 2 > (256 << 20)
-                       else "inputs smaller than L2: numbers are L2-warm",
-                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "config": workload_config(desc, n, batch, world, real),
+            "plan": {"path": info["path_name"], "inner_path": info["inner_path_name"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (tr["dram_bytes_per_sample"] * batch * n) if tr else None,
                          "traffic_source": tr["source"] if tr else None,

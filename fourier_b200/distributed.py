@@ -51,12 +51,18 @@ class CudaBackend:
         self.t = "float" if real == "f32" else "double"
         self.dtype = torch.complex64 if real == "f32" else torch.complex128
         self._plans = {}
+        self.launches = None   # set to 0 to have the methods below count the kernels they launch (bench.py)
+
+    def _count(self, n):
+        if self.launches is not None:
+            self.launches += n
 
     def _stream(self, x):
         return self.torch.cuda.current_stream(x.device).cuda_stream
 
     def _call(self, name, *args):
         rc = getattr(_lib.load(), f"fourier_b200_{name}_{self.t}")(*args)
+        self._count(1)
         if rc != 0:
             raise RuntimeError(f"fourier_b200_{name}_{self.t} failed: {_lib.last_error()}")
 
@@ -78,6 +84,8 @@ class CudaBackend:
         """In-place batched FFT over rows of length n (unscaled in both directions)."""
         from . import Transform
         self._plan(x, n).transform_in_place(x.view(-1, n), Transform.Fft if forward else Transform.UnscaledIfft)
+        if self.launches is not None:
+            self._count(self._plan(x, n).info()["last_launches"])
 
     def can_fuse(self, x, n, rows):
         """True if fft_rows_exchange() exists for rows of length n (two-pass plans, whole tiles of up to 32 rows)."""
@@ -88,6 +96,8 @@ class CudaBackend:
         register stage of the transform stores straight into the peers' buffers (csrc/dist_kernels.cuh)."""
         tw = None if twiddle is None else (twiddle[1], twiddle[2])
         self._plan(src, n).fft_rows_exchange(src.view(rows_loc, n), table, world * rows_loc, rank * rows_loc, forward, tw)
+        if self.launches is not None:
+            self._count(self._plan(src, n).info()["last_launches"])
 
     def transpose(self, src, dst, rows, cols):
         self._call("transpose", src.data_ptr(), dst.data_ptr(), 1, rows, cols, self._stream(src))
