@@ -344,7 +344,7 @@ class DistributedFft:
             return dst
         K = self._pieces(rows_loc) if fft_len else 1
         rows_k = rows_loc // K
-        main, side = torch.cuda.current_stream(), be.side_stream()
+        main, side = (torch.cuda.current_stream(), be.side_stream()) if K > 1 else (None, None)
         for k in range(K):
             if fft_len:
                 be.fft_rows(src[k * rows_k * cols:(k + 1) * rows_k * cols], fft_len, forward)
