@@ -1,6 +1,6 @@
 // dist_fft.cu -- row FFTs of the distributed six-step transform with the exchange folded into the store of their
 // last register stage (dist_kernels.cuh): pass 1 of the two-pass tile kernels as it is, pass 2 on tiles of C
-// adjacent transforms that store over NVLink peer memory.  Chunks alternate between the caller's stream and a
+// adjacent transforms that store over NVLink peer memory.  Chunks rotate over the caller's stream and
 // plan-owned ones (lanes), each with its own intermediate, so that pass 1 of one chunk (HBM reads, no NVLink
 // traffic) runs beside pass 2 of another (NVLink stores).
 #include <algorithm>
@@ -31,8 +31,9 @@ template <typename T> struct RowsExchangeCall {
 };
 
 // Tiles of twice as many transforms where the configuration's pass-2 tile has 16 (f32) / 8 (f64): a warp's store is then
-// one 256-byte run instead of two 128-byte pieces (NVLink moves 256-byte packets: measured 2 B200s, N = 2^28 ...).
-// Paddings are the bank-conflict-free ones (tools/emulate.cu).
+// one 256-byte run instead of two 128-byte pieces.  Measured (profiles/r02_rows_exchange_knobs.txt, r02_c5_modes_8gpu.json):
+// N = 2^30 on 2 GPUs 12.64 -> 12.27 ms, on 8 GPUs 5.13 -> 5.15 ms (no change), one GPU (three-pass path) no change.
+// Paddings are the bank-conflict-free ones (tools/emulate.cu).  FOURIER_B200_DIST_WIDE=0 selects the narrow tiles.
 template <class S, typename T> struct WideShape { using type = S; };
 template <> struct WideShape<twopass::Shape<8, 16, 16, 16, 2>, float> { using type = twopass::Shape<8, 16, 16, 32, 2>; };
 template <> struct WideShape<twopass::Shape<16, 16, 16, 16, 1>, float> { using type = twopass::Shape<16, 16, 16, 32, 1>; };
@@ -72,7 +73,7 @@ cudaError_t launch_rows_exchange(const RowsExchangeCall<T>& c) {
 }
 
 template <class G, bool WIDE, typename T> cudaError_t dispatch_rows_exchange(const RowsExchangeCall<T>& c) {
-  constexpr int MORE = 2;   // +1 .. 6 % on the three-pass path, neutral on the distributed one (gpurun_out/occ_ab.log)
+  constexpr int MORE = 2;   // +1 .. 6 % on the three-pass path, neutral on the distributed one (profiles/r02_rows_exchange_knobs.txt)
   if (c.fwd) return c.twiddle ? launch_rows_exchange<G, true, 1, MORE, WIDE>(c) : launch_rows_exchange<G, true, 0, MORE, WIDE>(c);
   return c.twiddle ? launch_rows_exchange<G, false, 2, MORE, WIDE>(c) : launch_rows_exchange<G, false, 0, MORE, WIDE>(c);
 }
