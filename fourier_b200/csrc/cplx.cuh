@@ -159,6 +159,67 @@ template <bool FWD, typename T> FB_HD void dft3(cpx<T> (&x)[3]) {
   x[2] = csub(t, r);
 }
 
+// Radix-9 butterfly, natural order in and out: 3 x 3 Cooley-Tukey on radix-3 butterflies.
+template <bool FWD, typename T> FB_HD void dft9(cpx<T> (&x)[9]) {
+  // n = 3*n1 + n2, k = k1 + 3*k2;  w_9^1, w_9^2, w_9^4 (forward = exp(-2 pi i k / 9))
+  constexpr T c1 = (T)0.76604444311897803520239265055542, s1 = (T)0.64278760968653932632264340990726;
+  constexpr T c2 = (T)0.17364817766693034885171662676931, s2 = (T)0.98480775301220805936674302458952;
+  constexpr T c4 = (T)-0.93969262078590838405410927732473, s4 = (T)0.34202014332566873304409961468226;
+  cpx<T> a[3][3];
+#pragma unroll
+  for (int n2 = 0; n2 < 3; ++n2) {
+    cpx<T> t[3] = {x[n2], x[3 + n2], x[6 + n2]};
+    dft3<FWD, T>(t);
+    a[n2][0] = t[0]; a[n2][1] = t[1]; a[n2][2] = t[2];
+  }
+  const T sg = FWD ? (T)-1 : (T)1;
+  a[1][1] = cmul(a[1][1], mk<T>(c1, sg * s1));
+  a[1][2] = cmul(a[1][2], mk<T>(c2, sg * s2));
+  a[2][1] = cmul(a[2][1], mk<T>(c2, sg * s2));
+  a[2][2] = cmul(a[2][2], mk<T>(c4, sg * s4));
+#pragma unroll
+  for (int k1 = 0; k1 < 3; ++k1) {
+    cpx<T> t[3] = {a[0][k1], a[1][k1], a[2][k1]};
+    dft3<FWD, T>(t);
+    x[k1] = t[0]; x[k1 + 3] = t[1]; x[k1 + 6] = t[2];
+  }
+}
+
+// Radix-27 butterfly, natural order in and out: 3 x 9 Cooley-Tukey (n = 9*n1 + n2, k = k1 + 3*k2) on the radix-3 and
+// radix-9 butterflies; twiddles w_27^{n2*k1}, n2 < 9, k1 < 3.  Outer pass of the {2,3}-smooth path (smooth3.cu).
+template <bool FWD, typename T> FB_HD void dft27(cpx<T> (&x)[27]) {
+  constexpr double c27[17] = {1.0, 0.97304487057982383883288517278469592, 0.89363264032341224819257418686665512,
+      0.76604444311897803520239265055541667, 0.59715859170278616485185216058395977, 0.39607976603915682369604339160974457,
+      0.1736481776669303488517166267693148, -0.058144828910475828538748016847071524, -0.28680323271109025310328017316715794,
+      -0.5, -0.68624163786873358572960499961753798, -0.83548781141293641965382617001958359,
+      -0.93969262078590838405410927732473147, -0.99323835774194298854789555219370434, -0.99323835774194298854789555219370434,
+      -0.93969262078590838405410927732473147, -0.83548781141293641965382617001958359};
+  constexpr double s27[17] = {0.0, 0.2306158707424401784501983492929391, 0.44879918020046217278504033473314362,
+      0.64278760968653932632264340990726343, 0.80212319275504378508329489193392513, 0.9182161068802740147589614153146366,
+      0.98480775301220805936674302458952301, 0.99830815827126820804782070878327753, 0.95798951231548887443737476695675462,
+      0.86602540378443864676372317075293618, 0.72737364157304869598717641766381552, 0.54950897807080603526278037405013392,
+      0.34202014332566873304409961468225958, 0.11609291412523022967566652338071147, -0.11609291412523022967566652338071147,
+      -0.34202014332566873304409961468225958, -0.54950897807080603526278037405013392};
+  cpx<T> a[3][9];   // a[k1][n2]
+  static_for<0, 9>([&](auto N2) FB_LAMBDA {
+    constexpr int n2 = decltype(N2)::value;
+    cpx<T> t[3] = {x[n2], x[9 + n2], x[18 + n2]};
+    dft3<FWD, T>(t);
+    a[0][n2] = t[0];
+    if constexpr (n2 == 0) {
+      a[1][n2] = t[1]; a[2][n2] = t[2];
+    } else {
+      a[1][n2] = cmul(t[1], mk<T>((T)c27[n2], (T)(FWD ? -s27[n2] : s27[n2])));
+      a[2][n2] = cmul(t[2], mk<T>((T)c27[2 * n2], (T)(FWD ? -s27[2 * n2] : s27[2 * n2])));
+    }
+  });
+  static_for<0, 3>([&](auto K1) FB_LAMBDA {
+    constexpr int k1 = decltype(K1)::value;
+    dft9<FWD, T>(a[k1]);
+    static_for<0, 9>([&](auto K2) FB_LAMBDA { x[k1 + 3 * decltype(K2)::value] = a[k1][decltype(K2)::value]; });
+  });
+}
+
 // Scale mode of a Transform code (fourier-algorithms/src/fft.rs:5-16, autosort/mod.rs:381-385).
 enum : int { kFft = 0, kIfft = 1, kUnscaledIfft = 2, kSqrtScaledFft = 3, kSqrtScaledIfft = 4 };
 inline bool transform_is_forward(int code) { return code == kFft || code == kSqrtScaledFft; }

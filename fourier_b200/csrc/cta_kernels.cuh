@@ -106,32 +106,6 @@ inline std::vector<cpx<T>> make_stage_twiddles(size_t len, const Stages& st, TW&
   return out;
 }
 
-// Radix-9 butterfly, natural order in and out: 3 x 3 Cooley-Tukey on radix-3 butterflies.
-template <bool FWD, typename T> FB_HD void dft9(cpx<T> (&x)[9]) {
-  // n = 3*n1 + n2, k = k1 + 3*k2;  w_9^1, w_9^2, w_9^4 (forward = exp(-2 pi i k / 9))
-  constexpr T c1 = (T)0.76604444311897803520239265055542, s1 = (T)0.64278760968653932632264340990726;
-  constexpr T c2 = (T)0.17364817766693034885171662676931, s2 = (T)0.98480775301220805936674302458952;
-  constexpr T c4 = (T)-0.93969262078590838405410927732473, s4 = (T)0.34202014332566873304409961468226;
-  cpx<T> a[3][3];
-#pragma unroll
-  for (int n2 = 0; n2 < 3; ++n2) {
-    cpx<T> t[3] = {x[n2], x[3 + n2], x[6 + n2]};
-    dft3<FWD, T>(t);
-    a[n2][0] = t[0]; a[n2][1] = t[1]; a[n2][2] = t[2];
-  }
-  const T sg = FWD ? (T)-1 : (T)1;
-  a[1][1] = cmul(a[1][1], mk<T>(c1, sg * s1));
-  a[1][2] = cmul(a[1][2], mk<T>(c2, sg * s2));
-  a[2][1] = cmul(a[2][1], mk<T>(c2, sg * s2));
-  a[2][2] = cmul(a[2][2], mk<T>(c4, sg * s4));
-#pragma unroll
-  for (int k1 = 0; k1 < 3; ++k1) {
-    cpx<T> t[3] = {a[0][k1], a[1][k1], a[2][k1]};
-    dft3<FWD, T>(t);
-    x[k1] = t[0]; x[k1 + 3] = t[1]; x[k1 + 6] = t[2];
-  }
-}
-
 // DFT of R register values, natural order in and out; R in {2, 3, 4, 8, 9, 16}.
 template <int R, bool FWD, typename T> FB_HD void dft_natural(cpx<T> (&x)[R]) {
   if constexpr (R == 3) {

@@ -27,7 +27,7 @@ namespace {
 template <typename T> struct RowsExchangeCall {
   const cpx<T>* scratch; const void* twa; void* const* outs; int nranks; size_t groups, out_ld, out_off;
   int twiddle, cb_shift; unsigned long long row0, n_total; bool fwd; cudaStream_t s;
-  size_t r0, out_bs; int rb_shift;
+  size_t r0, out_bs; int rb_shift; size_t rpb, rows_valid;
 };
 
 // Tiles of twice as many transforms where the configuration's pass-2 tile has 16 (f32) / 8 (f64): a warp's store is then
@@ -67,7 +67,7 @@ cudaError_t launch_rows_exchange(const RowsExchangeCall<T>& c) {
   for (int i = 0; i < kMaxPeers; ++i) a.outs.p[i] = i < c.nranks ? c.outs[i] : nullptr;
   a.out_ld = c.out_ld; a.out_off = c.out_off; a.row0 = c.row0; a.n_total = c.n_total;
   a.groups = (unsigned)c.groups; a.cb_shift = c.cb_shift;
-  a.r0 = c.r0; a.out_bs = c.out_bs; a.rb_shift = c.rb_shift;
+  a.r0 = c.r0; a.out_bs = c.out_bs; a.rb_shift = c.rb_shift; a.rpb = c.rpb; a.rows_valid = c.rows_valid;
   kernel<<<(unsigned)(c.groups * (size_t)G::N1), Tile::THREADS, X::smem, c.s>>>(a);
   return cudaGetLastError();
 }
@@ -88,7 +88,7 @@ template <typename T>
 cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, void* const* outs, int nranks,
                                         size_t out_ld, size_t out_off, int twiddle, unsigned long long row0,
                                         unsigned long long n_total, cudaStream_t s, size_t rows_per_batch,
-                                        size_t out_batch_stride) {
+                                        size_t out_batch_stride, size_t rows_valid) {
   if (path_ != Path::kTwoPass || !fast_ops_) {
     set_last_error("rows_exchange: the plan is not a two-pass plan (power-of-two sizes 2^11 .. 2^20 (f32), 2^9 .. 2^16 (f64))");
     return cudaErrorNotSupported;
@@ -104,13 +104,12 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
     return cudaErrorInvalidValue;
   }
   int rb_shift = 63;
+  size_t rpb = 0;                                   // rows per batch when that is not a power of two
   if (rows_per_batch) {
-    if ((rows_per_batch & (rows_per_batch - 1)) || rows % rows_per_batch) {
-      set_last_error("rows_exchange: rows per batch must be a power of two dividing the number of rows");
-      return cudaErrorInvalidValue;
-    }
-    for (rb_shift = 0; ((size_t)1 << rb_shift) < rows_per_batch; ++rb_shift) {}
+    if (rows_per_batch & (rows_per_batch - 1)) rpb = rows_per_batch;
+    else for (rb_shift = 0; ((size_t)1 << rb_shift) < rows_per_batch; ++rb_shift) {}
   }
+  if (rows_valid == 0 || rows_valid > rows) rows_valid = rows;
   if (rows == 0) return cudaSuccess;
   const auto* ops = static_cast<const twopass::TwoPassOps<T>*>(fast_ops_);
   int c2 = 0, c2w = 0;
@@ -118,8 +117,7 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
     c2 = decltype(g)::C2;
     c2w = ExchangeTile<decltype(g), true, T>::C;
   });
-  const bool wide = wide_wanted() && c2w != c2 && rows % (size_t)c2w == 0 &&
-                    (rows_per_batch == 0 || rows_per_batch % (size_t)c2w == 0);
+  const bool wide = wide_wanted() && c2w != c2 && rows % (size_t)c2w == 0;
   if (wide) c2 = c2w;
   if (c2 == 0 || rows % (size_t)c2) {
     set_last_error("rows_exchange: the number of rows must be a multiple of " + std::to_string(c2));
@@ -160,7 +158,7 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
     cudaStream_t st = lanes[lane];
     FB_CHECK(ops->pass1(in + b0 * n_, scratch, tw_a_.data(), (const C*)tw2_.data(), nb, forward, st));
     RowsExchangeCall<T> c{scratch, tw_b_.data(), outs, nranks, nb / (size_t)c2, out_ld, out_off, twiddle, cb_shift,
-                          row0, n_total, forward, st, b0, out_batch_stride, rb_shift};
+                          row0, n_total, forward, st, b0, out_batch_stride, rb_shift, rpb, rows_valid};
     cudaError_t e = cudaErrorNotSupported;
     twopass::visit_config<T>(n_, [&](auto g) {
       e = wide ? dispatch_rows_exchange<decltype(g), true>(c) : dispatch_rows_exchange<decltype(g), false>(c);
@@ -176,8 +174,10 @@ cudaError_t Plan<T>::exec_rows_exchange(const C* in, size_t rows, bool forward, 
 }
 
 template cudaError_t Plan<float>::exec_rows_exchange(const C*, size_t, bool, void* const*, int, size_t, size_t, int,
-                                                     unsigned long long, unsigned long long, cudaStream_t, size_t, size_t);
+                                                     unsigned long long, unsigned long long, cudaStream_t, size_t, size_t,
+                                                     size_t);
 template cudaError_t Plan<double>::exec_rows_exchange(const C*, size_t, bool, void* const*, int, size_t, size_t, int,
-                                                      unsigned long long, unsigned long long, cudaStream_t, size_t, size_t);
+                                                      unsigned long long, unsigned long long, cudaStream_t, size_t, size_t,
+                                                      size_t);
 
 }  // namespace fb200

@@ -56,6 +56,8 @@ struct RowsExchangeBody {
     unsigned long long r0;         // index of the chunk's first transform among the rows of the call
     unsigned long long out_bs;     // three-pass path (bigpow2.cu): rows come in batches of 2^rb_shift (one batch = one
     int rb_shift;                  //   long transform), batch b is stored out_bs elements further on; 63 = one batch
+    unsigned long long rpb;        // != 0: batches of rpb rows, not a power of two (outer radix 3 / 9 / 27)
+    unsigned long long rows_valid; // rows of the call that exist: the last tile may be padding (nothing is stored for it)
     unsigned groups;               // transforms of the chunk / C
     int cb_shift;                  // log2(cb): destination rank of output k is k >> cb_shift
   };
@@ -75,7 +77,9 @@ struct RowsExchangeBody {
     const int col = Tile::template col_of<kMapCF>(t), u = Tile::template u_of<kMapCF>(t);
     const unsigned long long r = (unsigned long long)g * C + col;          // transform of the chunk
     const unsigned long long rc = a.r0 + r;                                // ... of the call
-    const unsigned long long dcol = (rc >> a.rb_shift) * a.out_bs + a.out_off + (rc & ((1ull << a.rb_shift) - 1));
+    const unsigned long long bidx = a.rpb ? rc / a.rpb : rc >> a.rb_shift;
+    const unsigned long long dcol = bidx * a.out_bs + a.out_off + (a.rpb ? rc - bidx * a.rpb : rc & ((1ull << a.rb_shift) - 1));
+    const bool valid = rc < a.rows_valid;
     const unsigned long long mask = (1ull << a.cb_shift) - 1;
     [[maybe_unused]] double sr = 1.0, si = 0.0;
     [[maybe_unused]] unsigned long long rg = 0;
@@ -103,7 +107,7 @@ struct RowsExchangeBody {
           wr = nr;
         }
         V* dst = reinterpret_cast<V*>(a.outs.p[k >> a.cb_shift]);
-        dst[(k & mask) * a.out_ld + dcol] = val;
+        if (valid) dst[(k & mask) * a.out_ld + dcol] = val;
       });
     });
   }

@@ -80,5 +80,50 @@ __global__ void __launch_bounds__(Tile::THREADS, MINB) column_kernel(const typen
   Body::phase2(f, a, blockIdx.x, threadIdx.x, smem);
 }
 
+// Outer pass of length B = 3, 9 or 27 for N = B * Nb (Nb a two-pass power of two): the radix-3 stages of the
+// reference (autosort/mod.rs:20-21, butterfly.rs:9-22) taken FIRST, as one in-register DFT_B per column -- one thread
+// per column nb, so every access of a warp is a 256-byte run -- followed by the twiddle w_N^{nb * ka} (one sincospi
+// in double per thread, powers by recurrence) and the scale.  The rows then run as in the power-of-two case.
+template <typename T, int B, bool FWD_>
+struct Radix3ColumnBody {
+  using V = cpx<T>;
+  static constexpr bool FWD = FWD_;
+  struct Args {
+    const V* in; V* out;
+    unsigned long long nb;        // row length = pitch of the samples of one column
+    unsigned long long n_total;   // N = B * nb
+    unsigned long long count;     // columns of the call (batch * nb)
+    T scale;
+  };
+  static FB_HD void run(const Args& a, unsigned long long idx) {
+    if (idx >= a.count) return;
+    const unsigned long long b = idx / a.nb, col = idx - b * a.nb;
+    const V* src = a.in + b * a.n_total + col;
+    V x[B];
+#pragma unroll
+    for (int i = 0; i < B; ++i) x[i] = src[(unsigned long long)i * a.nb];
+    if constexpr (B == 3) dft3<FWD, T>(x);
+    else if constexpr (B == 9) dft9<FWD, T>(x);
+    else dft27<FWD, T>(x);
+    double sr, si;
+    dist::unit_root(col, a.n_total, &sr, &si);
+    if (FWD) si = -si;
+    double wr = (double)a.scale, wi = 0.0;
+    V* dst = a.out + b * a.n_total + col;
+    static_for<0, B>([&](auto K) FB_LAMBDA {
+      constexpr int ka = decltype(K)::value;
+      dst[(unsigned long long)ka * a.nb] = cmul(x[ka], mk<T>((T)wr, (T)wi));
+      const double nr = wr * sr - wi * si;
+      wi = wr * si + wi * sr;
+      wr = nr;
+    });
+  }
+};
+
+template <class Body>
+__global__ void __launch_bounds__(256) radix3_column_kernel(const typename Body::Args a) {
+  Body::run(a, (unsigned long long)blockIdx.x * 256 + threadIdx.x);
+}
+
 }  // namespace outer
 }  // namespace fb200

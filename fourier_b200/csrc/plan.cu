@@ -138,7 +138,9 @@ const char* Plan<T>::kernel_name() const {
     case Path::kBluestein: return "chirp / pointwise kernels around the inner plan's kernels";
     case Path::kBluesteinFused: return cta_chirp_ ? "cta::cta_fft_kernel (chirp mode)" : "onchip::bluestein_fused_kernel";
     case Path::kCta: return "cta::cta_fft_kernel";
-    case Path::kThreePass: return "outer::column_kernel + twopass::tile_kernel (pass 1) + dist::rows_exchange_kernel (transposed store)";
+    case Path::kThreePass:
+      return outer_radix3_ ? "outer::radix3_column_kernel + twopass::tile_kernel (pass 1) + dist::rows_exchange_kernel (transposed store)"
+                           : "outer::column_kernel + twopass::tile_kernel (pass 1) + dist::rows_exchange_kernel (transposed store)";
   }
   return "?";
 }
@@ -174,6 +176,12 @@ cudaError_t Plan<T>::init(size_t n, int device, bool allow_fast_paths) {
     }
     // everything else that fits two shared-memory buffers: one kernel, one HBM round trip
     if (allow_fast_paths && init_cta(n) == cudaSuccess) { path_ = Path::kCta; return cudaSuccess; }
+    // 3^b * 2^k (b <= 3) with a two-pass power of two: outer radix-3^b pass + two-pass rows (bigpow2.cu)
+    const char* tp3 = std::getenv("FOURIER_B200_TWOPASS");   // =0 (experiment knob): measure the per-stage path instead
+    if (allow_fast_paths && !pow2 && !(tp3 && atoi(tp3) == 0) && init_threepass_radix3() == cudaSuccess) {
+      path_ = Path::kThreePass;
+      return cudaSuccess;
+    }
     path_ = Path::kGlobalStages;
     return init_global_stages();
   }

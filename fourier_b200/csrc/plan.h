@@ -110,10 +110,12 @@ class Plan {
   // buffers: outs[q][c * out_ld + out_off + r] = X_r[q * cb + c] * w_Ntot^{(row0 + r) * (q * cb + c)}, cb = size() / nranks
   // (what launch_exchange() delivers after exec_device() on the same rows).  Two-pass sizes only; `in` is left intact.
   // rows_per_batch != 0 (three-pass path): the rows come in batches of that many, batch b goes out_batch_stride
-  // elements further on: outs[q][b * out_batch_stride + c * out_ld + out_off + r % rows_per_batch].
+  // elements further on: outs[q][b * out_batch_stride + c * out_ld + out_off + r % rows_per_batch]; rows_valid != 0:
+  // only the first rows_valid rows exist, the rest pads the last tile (read, transformed, not stored).
   cudaError_t exec_rows_exchange(const C* in, size_t rows, bool forward, void* const* outs, int nranks, size_t out_ld,
                                  size_t out_off, int twiddle, unsigned long long row0, unsigned long long n_total,
-                                 cudaStream_t stream, size_t rows_per_batch = 0, size_t out_batch_stride = 0);
+                                 cudaStream_t stream, size_t rows_per_batch = 0, size_t out_batch_stride = 0,
+                                 size_t rows_valid = 0);
 
   // Number of kernel launches the last exec_* call issued (bench.py reports it).
   unsigned long long launches() const { return launches_; }
@@ -137,6 +139,7 @@ class Plan {
   cudaError_t init_onchip();
   cudaError_t init_twopass();
   cudaError_t init_bigpow2();
+  cudaError_t init_threepass_radix3();
   cudaError_t init_cta(size_t len);   // len = n_, or the Bluestein inner size
   cudaError_t init_bluestein(bool allow_fast_paths);
   cudaError_t init_bluestein_fused(const std::vector<double>& chirp_re, const std::vector<double>& chirp_im,
@@ -158,6 +161,7 @@ class Plan {
   size_t chunk_ = 0;                 // transforms per L2-resident chunk (two-pass)
   const void* fused_ops_ = nullptr;  // FusedOps<T>: persistent single-launch variant
   int ring_ = 0, lag_ = 0, sm_count_ = 148;
+  int outer_radix3_ = 0;             // kThreePass: 3 / 9 / 27 = the outer pass is a radix-3 DFT (N = 3^b * 2^k), 0 = power of two
   DeviceBuffer counters_, tbase_, tstep_, trace_;
 
   // kCta (and kBluesteinFused through the CTA kernel): on-chip transform length, radices_ and wtab_ as above

@@ -142,6 +142,33 @@ def test_three_pass_path_above_the_two_pass_sizes(real, n):
         assert rel_err(first, gpu_transform(gen, x, T.Fft)) < TOL[real]
 
 
+@pytest.mark.parametrize("real,n", [("f32", 3 << 13), ("f32", 9 << 14), ("f32", 27 << 11), ("f32", 3 << 18), ("f32", 27 << 16),
+                                    ("f64", 3 << 12), ("f64", 9 << 13), ("f64", 27 << 10)])
+def test_three_pass_path_with_an_outer_radix3_pass(real, n):
+    """N = 3^b * 2^k (b <= 3) above the CTA kernel's shared memory: outer radix-3 / 9 / 27 pass + two-pass rows with the
+    transposed store (csrc/bigpow2.cu).  3 / 9 / 27 rows per transform pad the 32-row tiles of the row kernel: batches of
+    1, 2 and 5 transforms; every Transform code against the oracle; in place; the independent per-stage path."""
+    import torch
+    p = create(real, n)
+    assert p.info()["path_name"] == "threepass" and p.info()["n1"] in (3, 9, 27) and p.info()["n1"] * p.info()["n2"] == n
+    assert "radix3_column_kernel" in p.kernel_name()
+    x = O.fill_input(5, n, NP[real], first_transform=9)
+    want = {int(c): O.transform(x, int(c)) for c in (T.Fft, T.Ifft, T.UnscaledIfft, T.SqrtScaledFft, T.SqrtScaledIfft)}
+    for code, w in want.items():
+        got = gpu_transform(p, x, T(code))
+        e = rel_err(got, w)
+        assert e < TOL[real], (n, code, e)
+    first = gpu_transform(p, x, T.Fft)
+    for b in (1, 2):
+        assert np.array_equal(gpu_transform(p, np.ascontiguousarray(x[:b]), T.Fft), first[:b])
+    xd = torch.from_numpy(x).cuda()
+    p.transform_in_place(xd, T.Fft)
+    assert np.array_equal(xd.cpu().numpy(), first)
+    gen = create(real, n, general=True)
+    assert gen.info()["path_name"] == "global_stages"
+    assert rel_err(first, gpu_transform(gen, x, T.Fft)) < TOL[real]
+
+
 @pytest.mark.parametrize("real,n", [("f32", 1_500_001), ("f64", 100_003)])
 def test_bluestein_around_a_three_pass_inner_plan(real, n):
     """Bluestein sizes whose inner power of two (2^22 f32, 2^18 f64) lies above the two-pass kernels."""

@@ -541,7 +541,7 @@ static int check_rows_exchange(const char* name, int P, double tol) {
   a.scratch = scratch.data(); a.twa = twa2.data();
   for (int q = 0; q < kMaxPeers; ++q) a.outs.p[q] = q < P ? dst[q].data() : nullptr;
   a.out_ld = out_ld; a.out_off = out_off; a.row0 = row0; a.n_total = n_total; a.groups = (unsigned)(rows / Tile::C);
-  a.r0 = 0; a.out_bs = 0; a.rb_shift = 63;
+  a.r0 = 0; a.out_bs = 0; a.rb_shift = 63; a.rpb = 0; a.rows_valid = ~0ull;
   a.cb_shift = 0;
   while ((1L << a.cb_shift) < cb) ++a.cb_shift;
   run_body<Body, Tile, LayX>(a, (long)a.groups * N1);
@@ -607,7 +607,7 @@ static int check_threepass(const char* name, double tol) {
   a.scratch = scratch.data(); a.twa = twa2.data();
   for (int q = 0; q < kMaxPeers; ++q) a.outs.p[q] = q == 0 ? out.data() : nullptr;
   a.out_ld = Na; a.out_off = 0; a.row0 = 0; a.n_total = 0; a.groups = (unsigned)(B * Na / Tile::C);
-  a.r0 = 0; a.out_bs = N; a.rb_shift = 0;
+  a.r0 = 0; a.out_bs = N; a.rb_shift = 0; a.rpb = 0; a.rows_valid = ~0ull;
   while ((1L << a.rb_shift) < Na) ++a.rb_shift;
   a.cb_shift = 0;
   while ((1L << a.cb_shift) < Nb) ++a.cb_shift;
@@ -627,8 +627,67 @@ static int check_threepass(const char* name, double tol) {
   return !(maxerr / maxref < tol);
 }
 
+// ---- three-pass path with an outer radix-3 / 9 / 27 pass (N = 3^b * 2^k, bigpow2.cu) ---------------------------------
+template <typename T, int B, class Cfg, bool FWD>
+static int check_threepass_radix3(const char* name, double tol) {
+  const long Nb = Cfg::N, N = B * Nb, BATCH = 2;
+  using Tile = typename Cfg::template Tile2<FWD>;
+  const long rows = BATCH * B, rows_pad = (rows + Tile::C - 1) / Tile::C * Tile::C;
+  std::vector<cpx<T>> x(BATCH * N), work(rows_pad * Nb, mk<T>((T)NAN, (T)NAN)), scratch(rows_pad * Nb), out(BATCH * N, mk<T>((T)777, (T)777));
+  fill<T>(x, 41 + B);
+  using BodyO = outer::Radix3ColumnBody<T, B, FWD>;
+  typename BodyO::Args ao;
+  ao.in = x.data(); ao.out = work.data(); ao.nb = Nb; ao.n_total = N; ao.count = BATCH * Nb; ao.scale = (T)0.5;
+  for (long i = 0; i < BATCH * Nb + 7; ++i) BodyO::run(ao, i);          // a few threads beyond the end, as the grid has
+  const auto* ops = Cfg::ops();
+  auto twa1 = make_twa<T>(ops->ra1, ops->rb1), twa2 = make_twa<T>(ops->ra2, ops->rb2);
+  std::vector<cpx<T>> tw2(Nb);
+  for (long k1 = 0; k1 < Cfg::N1; ++k1)
+    for (long c = 0; c < Cfg::N2; ++c) {
+      double re, im;
+      host_twiddle((size_t)(k1 * c), (size_t)Nb, &re, &im);
+      tw2[k1 * Cfg::N2 + c] = mk<T>((T)re, (T)im);
+    }
+  run_body<typename Cfg::template Body1<FWD>, typename Cfg::template Tile1<FWD>, typename Cfg::Lay1>(
+      Cfg::template args1<FWD>(work.data(), scratch.data(), twa1.data(), tw2.data()), rows_pad * (Cfg::N2 / Cfg::template Tile1<FWD>::C));
+  using Body = dist::RowsExchangeBody<Tile, typename Cfg::Lay2, Cfg::N1, Cfg::N2, 0>;
+  typename Body::Args a;
+  a.scratch = scratch.data(); a.twa = twa2.data();
+  for (int q = 0; q < kMaxPeers; ++q) a.outs.p[q] = q == 0 ? out.data() : nullptr;
+  a.out_ld = B; a.out_off = 0; a.row0 = 0; a.n_total = 0; a.groups = (unsigned)(rows_pad / Tile::C);
+  a.r0 = 0; a.out_bs = N; a.rb_shift = 63; a.rpb = B; a.rows_valid = rows;
+  a.cb_shift = 0;
+  while ((1L << a.cb_shift) < Nb) ++a.cb_shift;
+  run_body<Body, Tile, typename Cfg::Lay2>(a, (long)a.groups * Cfg::N1);
+  double maxref = 0, maxerr = 0;
+  for (long bb = 0; bb < BATCH; ++bb) {                                   // naive DFT of a few outputs + an FFT-free check
+    std::vector<double> re(N), im(N);
+    for (long i = 0; i < N; ++i) { re[i] = x[bb * N + i].x; im[i] = x[bb * N + i].y; }
+    for (long k = 0; k < N; k += (k < 40 ? 1 : N / 97 + 1)) {
+      double sr = 0, si = 0;
+      for (long n = 0; n < N; ++n) {
+        const double ang = (FWD ? -2.0 : 2.0) * M_PI * (double)((k * n) % N) / (double)N;
+        sr += re[n] * std::cos(ang) - im[n] * std::sin(ang);
+        si += re[n] * std::sin(ang) + im[n] * std::cos(ang);
+      }
+      maxref = std::max(maxref, std::hypot(sr * 0.5, si * 0.5));
+      maxerr = std::max(maxerr, std::hypot(out[bb * N + k].x - sr * 0.5, out[bb * N + k].y - si * 0.5));
+    }
+  }
+  long untouched = 0, nans = 0;
+  for (auto& v : out) { untouched += v.x == (T)777; nans += std::isnan(v.x); }
+  printf("%s three-pass %d x %ld (%s): max rel err %.3e (tol %.1e), unwritten %ld, nan %ld %s\n", name, B, Nb, FWD ? "forward" : "inverse",
+         maxerr / maxref, tol, untouched, nans, maxerr / maxref < tol && untouched == 0 && nans == 0 ? "OK" : "FAIL");
+  return !(maxerr / maxref < tol && untouched == 0 && nans == 0);
+}
+
 int main() {
   int bad = 0;
+  bad += check_threepass_radix3<float, 3, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, true>("f32 3*2^11", 2e-6);
+  bad += check_threepass_radix3<float, 9, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, false>("f32 9*2^11", 2e-6);
+  bad += check_threepass_radix3<float, 27, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, true>("f32 27*2^11", 2e-6);
+  bad += check_threepass_radix3<double, 27, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, false>("f64 27*2^9", 1e-14);
+  bad += check_threepass_radix3<double, 3, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, true>("f64 3*2^9", 1e-14);
   bad += check_threepass<float, Shape<4, 8, 8, 32, 0>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, true>("f32 2^16", 2e-6);
   bad += check_threepass<float, Shape<8, 16, 16, 16, 0>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, false>("f32 2^18", 2e-6);
   bad += check_threepass<double, Shape<4, 4, 4, 16, 0>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, true>("f64 2^13", 5e-15);
