@@ -43,8 +43,8 @@ template <typename T, class S, int MINB> struct ColumnImpl {
   static cudaError_t run(const cpx<T>* in, cpx<T>* out, const void* twa, size_t nb, size_t batch, T scale, cudaStream_t s) {
     using Body = outer::ColumnBody<Tile<FWD>, Lay>;
     auto kernel = &outer::column_kernel<Body, Tile<FWD>, MINB>;
-    static cudaError_t prepared = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (prepared != cudaSuccess) return prepared;
+    static std::atomic<unsigned long long> prepared{0};
+    if (cudaError_t e = ensure_dynamic_smem(kernel, smem, prepared)) return e;
     typename Body::Args a;
     a.in = in; a.out = out; a.twa = (const TwPair<T>*)twa;
     a.nb = nb; a.n_total = (unsigned long long)S::L * nb; a.tiles = (unsigned)(nb / S::C); a.scale = scale;

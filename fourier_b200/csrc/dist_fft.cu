@@ -58,9 +58,8 @@ cudaError_t launch_rows_exchange(const RowsExchangeCall<T>& c) {
   using Tile = typename X::template Tile<FWD>;
   using Body = dist::RowsExchangeBody<Tile, typename X::Lay, G::N1, G::N2, TW>;
   auto kernel = &dist::rows_exchange_kernel<Body, Tile, X::kMinBlocks + (WIDE ? MORE / 2 : MORE)>;
-  static cudaError_t prepared =
-      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X::smem);
-  if (prepared != cudaSuccess) return prepared;
+  static std::atomic<unsigned long long> prepared{0};
+  if (cudaError_t e = ensure_dynamic_smem(kernel, X::smem, prepared)) return e;
   typename Body::Args a;
   a.scratch = c.scratch;
   a.twa = (const TwPair<T>*)c.twa;
