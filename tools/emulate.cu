@@ -692,6 +692,14 @@ int main() {
   bad += check_threepass<float, Shape<8, 16, 16, 16, 0>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, false>("f32 2^18", 2e-6);
   bad += check_threepass<double, Shape<4, 4, 4, 16, 0>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, true>("f64 2^13", 5e-15);
   bad += check_threepass<double, Shape<8, 16, 16, 8, 4>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, false>("f64 2^16", 5e-15);
+  // the remaining outer-pass shapes of bigpow2.cu's column_lookup
+  bad += check_threepass<float, Shape<8, 8, 8, 32, 0>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, true>("f32 2^17", 2e-6);
+  bad += check_threepass<float, Shape<16, 16, 16, 16, 0>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, true>("f32 2^19", 2e-6);
+  bad += check_threepass<float, Shape<16, 32, 32, 8, 8>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, false>("f32 2^20", 2e-6);
+  bad += check_threepass<float, Shape<32, 32, 32, 8, 8>, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, true>("f32 2^21", 2e-6);
+  bad += check_threepass<double, Shape<4, 8, 8, 16, 0>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, true>("f64 2^14", 5e-15);
+  bad += check_threepass<double, Shape<8, 8, 8, 16, 0>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, false>("f64 2^15", 5e-15);
+  bad += check_threepass<double, Shape<16, 16, 16, 8, 4>, TwoPassG<double, Shape<4, 4, 4, 16, 0>, Shape<4, 8, 8, 16, 2>, 4, 4>, true>("f64 2^17", 5e-15);
   bad += check_rows_exchange<float, TwoPassG<float, Shape<4, 8, 8, 32, 0>, Shape<8, 8, 8, 32, 2>, 4, 4>, 1>("f32 2^11", 4, 2e-6);
   bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>, 1>("f32 2^14", 8, 2e-6);
   bad += check_rows_exchange<float, TwoPassG<float, Shape<8, 16, 16, 16, 0>, Shape<8, 16, 16, 16, 2>, 4, 4>, 2>("f32 2^14", 2, 2e-6);
